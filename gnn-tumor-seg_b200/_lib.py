@@ -1,0 +1,151 @@
+"""ctypes binding of libgts.so (C-ABI declared in include/gts.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (or
+``make -C gnn-tumor-seg_b200/csrc``).  There is deliberately no fallback: if the
+shared object is missing or a CUDA device is absent, every compute entry point
+raises — the product never computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgts.so")
+
+GTS_OK = 0
+ACT_NONE, ACT_RELU, ACT_MASK_POS = 0, 1, 2
+GEMM_FP32, GEMM_TF32, GEMM_TF32X3 = 0, 1, 2
+GEMM_MODES = {"fp32": GEMM_FP32, "tf32": GEMM_TF32, "tf32x3": GEMM_TF32X3}
+
+c_f32p = C.c_void_p
+c_i32p = C.c_void_p
+c_i64p = C.c_void_p
+c_i16p = C.c_void_p
+c_stream = C.c_void_p
+
+
+class GemmNtArgs(C.Structure):
+    """struct gts_gemm_nt_args (include/gts.h)."""
+    _fields_ = [
+        ("A1", C.c_void_p), ("lda1", C.c_int64), ("K1", C.c_int32),
+        ("A2", C.c_void_p), ("lda2", C.c_int64), ("K2", C.c_int32),
+        ("B1", C.c_void_p), ("ldb1", C.c_int64),
+        ("B2", C.c_void_p), ("ldb2", C.c_int64),
+        ("bias", C.c_void_p),
+        ("aux", C.c_void_p), ("ldaux", C.c_int64),
+        ("C", C.c_void_p), ("ldc", C.c_int64),
+        ("M", C.c_int32), ("N", C.c_int32),
+        ("act", C.c_int32), ("mode", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); mirrors include/gts.h one to one
+_SIGNATURES = {
+    "gts_version": (C.c_int, []),
+    "gts_last_error": (C.c_char_p, []),
+    "gts_device_info": (C.c_int, [C.POINTER(C.c_int32)] * 3),
+    "gts_batch_edges": (C.c_int, [c_i32p, c_i32p, C.c_int64, c_i64p, c_i32p, C.c_int32, c_i32p, c_i32p, c_stream]),
+    "gts_csr_build_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "gts_csr_build": (C.c_int, [c_i32p, c_i32p, C.c_int64, C.c_int32, c_i32p, c_i32p, c_i32p,
+                                C.c_void_p, C.c_size_t, c_stream]),
+    "gts_edge_perm_compose": (C.c_int, [c_i32p, c_i32p, C.c_int64, c_i32p, c_i32p, c_stream]),
+    "gts_gemm_nt": (C.c_int, [C.POINTER(GemmNtArgs), c_stream]),
+    "gts_gemm_tn_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64, C.c_int32]),
+    "gts_gemm_tn": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_int32, C.c_int32,
+                              C.c_int64, C.c_int32, C.c_void_p, C.c_size_t, c_stream]),
+    "gts_colsum_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "gts_colsum": (C.c_int, [c_f32p, C.c_int64, C.c_int64, C.c_int32, c_f32p, C.c_void_p, C.c_size_t, c_stream]),
+    "gts_transpose": (C.c_int, [c_f32p, C.c_int64, C.c_int32, C.c_int32, c_f32p, C.c_int64, c_stream]),
+    "gts_segmax_fwd": (C.c_int, [c_f32p, C.c_int64, c_i32p, c_i32p, C.c_int32, C.c_int32, c_f32p, C.c_int64,
+                                 c_i32p, C.c_int64, c_stream]),
+    "gts_segmax_bwd": (C.c_int, [c_f32p, C.c_int64, c_i32p, C.c_int64, C.c_int32, C.c_int32, c_f32p, C.c_int64,
+                                 C.c_int32, c_stream]),
+    "gts_segmax_bwd_det": (C.c_int, [c_f32p, C.c_int64, c_i32p, C.c_int64, c_i32p, c_i32p, C.c_int32, C.c_int32,
+                                     c_f32p, C.c_int64, c_stream]),
+    "gts_segsum_fwd": (C.c_int, [c_f32p, C.c_int64, c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_f32p,
+                                 C.c_int64, c_stream]),
+    "gts_segsum_bwd": (C.c_int, [c_f32p, C.c_int64, c_i32p, c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int32,
+                                 c_f32p, C.c_int64, c_stream]),
+    "gts_mask_pos": (C.c_int, [c_f32p, c_f32p, C.c_int64, c_f32p, c_stream]),
+    "gts_ce_weighted": (C.c_int, [c_f32p, C.c_int64, c_i64p, c_f32p, C.c_int32, C.c_int32, c_f32p, c_f32p,
+                                  C.c_int64, c_stream]),
+    "gts_scale_by_inv": (C.c_int, [c_f32p, C.c_int64, C.c_float, c_f32p, c_stream]),
+    "gts_argmax_rows": (C.c_int, [c_f32p, C.c_int64, C.c_int32, C.c_int32, c_i32p, c_stream]),
+    "gts_project_nodes": (C.c_int, [c_i16p, C.c_int64, c_i64p, C.c_int32, c_i64p, c_i32p, c_stream]),
+    "gts_project_labels": (C.c_int, [c_i16p, C.c_int32, C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p, c_i32p,
+                                     C.c_int32, c_i16p, C.c_int32, c_i16p, C.c_int32, C.c_int32, C.c_int32,
+                                     c_i32p, c_stream]),
+    "gts_project_logits": (C.c_int, [c_i16p, C.c_int64, c_f32p, C.c_int64, C.c_int32, C.c_int32, c_f32p, c_f32p,
+                                     c_i32p, c_stream]),
+    "gts_gat_scores": (C.c_int, [c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, c_f32p,
+                                 c_f32p, c_stream]),
+    "gts_gat_fwd": (C.c_int, [c_f32p, C.c_int64, c_f32p, c_f32p, c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int32,
+                              C.c_float, c_f32p, C.c_int64, c_f32p, C.c_int32, c_f32p, C.c_int64, c_f32p, c_f32p,
+                              c_i32p, c_stream]),
+    "gts_gat_act_bwd": (C.c_int, [c_f32p, c_f32p, C.c_int64, C.c_int32, c_f32p, c_stream]),
+    "gts_gat_bwd_dst": (C.c_int, [c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_i32p, c_f32p,
+                                  C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float, c_f32p, c_f32p, c_stream]),
+    "gts_gat_bwd_src": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_i32p, c_i32p, c_f32p, C.c_int64,
+                                  c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                  c_f32p, C.c_int64, c_f32p, c_stream]),
+    "gts_gat_attn_grad_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "gts_gat_attn_grad": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int32, C.c_int32, C.c_int32, c_f32p,
+                                    C.c_void_p, C.c_size_t, c_stream]),
+    "gts_adamw_step": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_float, C.c_float, C.c_float,
+                                 C.c_float, C.c_float, C.c_int32, C.c_float, c_f32p, c_stream]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+class GtsError(RuntimeError):
+    """A libgts.so call returned a non-zero status."""
+
+
+def lib_available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def load():
+    """Load libgts.so (once) and bind every symbol of include/gts.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GtsError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"or `make -C {os.path.join(_HERE, 'csrc')}`. There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != GTS_OK:
+        msg = load().gts_last_error()
+        raise GtsError(f"{what or 'libgts'} failed (status {rc}): {msg.decode() if msg else ''}")
+
+
+def require_cuda(*tensors) -> None:
+    """Fail loudly if a tensor is not on a CUDA device (no CPU path exists)."""
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise GtsError("gnn_tumor_seg_b200 computes only on a CUDA device (B200, sm_100a); "
+                           f"got a tensor on {t.device}. Move inputs with .to('cuda').")
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

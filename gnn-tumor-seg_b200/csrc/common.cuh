@@ -1,0 +1,66 @@
+// common.cuh — shared helpers for libgts.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include "../../include/gts.h"
+
+namespace gts {
+
+void set_error(const char* fmt, ...);
+
+#define GTS_CHECK_ARG(cond, ...)                \
+  do {                                          \
+    if (!(cond)) {                              \
+      ::gts::set_error(__VA_ARGS__);            \
+      return GTS_ERR_INVALID;                   \
+    }                                           \
+  } while (0)
+
+#define GTS_CUDA(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      ::gts::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,         \
+                       cudaGetErrorString(_e));                                     \
+      return GTS_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+#define GTS_LAUNCH_CHECK() GTS_CUDA(cudaGetLastError())
+
+inline cudaStream_t as_stream(gts_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int sm_count();   // cached SM count of the current device
+
+template <typename T>
+__host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// 128-bit read-only global load that does not allocate in L1 (streaming rows).
+__device__ __forceinline__ float4 ldg_nc_na(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+// 128-bit read-only global load through L1 (gathered rows that neighbouring
+// warps re-read).
+__device__ __forceinline__ float4 ldg_nc(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_na(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void stg_na(int4* p, const int4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+}  // namespace gts

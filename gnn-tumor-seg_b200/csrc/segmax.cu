@@ -1,0 +1,371 @@
+// segmax.cu — K2 / K2b: neighbour max-aggregation over the in-edge CSR and its
+// backward.  Replaces DGL update_all(copy_src, max) (gspmm copy_lhs/max with
+// arg outputs) and the scatter_add_ of its autograd inside SAGEConv('pool')
+// (reference model/networks.py:35).
+//
+// Forward: one warp (or a 2^k-lane slice of a warp for narrow rows) per
+// destination node; lane l owns float4 column chunks l, l+LPN, ...; the row's
+// neighbour ids are read coalesced once and broadcast by shuffle; neighbour
+// rows are gathered with 128-bit loads, four neighbours in flight, and folded
+// in CSR order with a strictly-greater test, so the FIRST maximum wins
+// (bit-exact arg-max vs the oracle).  HBM-bound: algorithmic bytes
+// 4*(N*D read + N*D write + N*D argmax + (N+1) + E).
+#include "common.cuh"
+#include <cfloat>
+
+namespace gts {
+
+constexpr int kSegThreads = 256;
+
+__device__ __forceinline__ void fold_max(float4& best, int4& arg, const float4& v, int u) {
+  if (v.x > best.x) { best.x = v.x; arg.x = u; }
+  if (v.y > best.y) { best.y = v.y; arg.y = u; }
+  if (v.z > best.z) { best.z = v.z; arg.z = u; }
+  if (v.w > best.w) { best.w = v.w; arg.w = u; }
+}
+
+// LPN lanes per node (power of two <= 32), VEC float4 chunks per lane:
+// covers D4 = D/4 <= LPN*VEC.
+template <int LPN, int VEC, bool WRITE_ARG>
+__global__ void __launch_bounds__(kSegThreads)
+segmax_fwd_vec_kernel(const float* __restrict__ P, int64_t ldp, const int32_t* __restrict__ indptr,
+                      const int32_t* __restrict__ indices, int32_t N, int32_t D4,
+                      float* __restrict__ neigh, int64_t ldn, int32_t* __restrict__ argmax, int64_t ldarg) {
+  constexpr int NPW = 32 / LPN;   // nodes per warp
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPN;
+  const int slot = lane / LPN;
+  const unsigned full = 0xffffffffu;
+  const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+
+  for (int64_t v0 = warp_global * NPW; v0 < N; v0 += n_warps * NPW) {
+    const int64_t v = v0 + slot;
+    const bool live = v < N;
+    int32_t beg = 0, end = 0;
+    if (live) { beg = indptr[v]; end = indptr[v + 1]; }
+    float4 best[VEC];
+    int4 arg[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      best[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      arg[j] = make_int4(-1, -1, -1, -1);
+    }
+    // longest row among the nodes sharing this warp (uniform loop bound)
+    int32_t deg = end - beg;
+    int32_t max_deg = deg;
+    if (NPW > 1) {
+#pragma unroll
+      for (int o = 16; o >= LPN; o >>= 1) max_deg = max(max_deg, __shfl_xor_sync(full, max_deg, o));
+    }
+    for (int32_t base = 0; base < max_deg; base += LPN) {
+      // each LPN-lane group reads LPN neighbour ids coalesced
+      const int32_t my_idx = (base + sub < deg) ? indices[beg + base + sub] : -1;
+      const int32_t cnt = min(LPN, max_deg - base);
+      for (int32_t j = 0; j < cnt; j += 4) {
+        int32_t u[4];
+        float4 r[4][VEC];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          // j+q < LPN holds whenever LPN >= 4; LPN < 4 wraps harmlessly onto -1 lanes via the cnt test
+          u[q] = __shfl_sync(full, my_idx, (slot * LPN) + ((j + q) % LPN));
+          if (j + q >= cnt) u[q] = -1;
+#pragma unroll
+          for (int c = 0; c < VEC; ++c) {
+            const int chunk = sub + c * LPN;
+            if (u[q] >= 0 && chunk < D4)
+              r[q][c] = ldg_nc(reinterpret_cast<const float4*>(P + (int64_t)u[q] * ldp) + chunk);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (u[q] >= 0) {
+#pragma unroll
+            for (int c = 0; c < VEC; ++c)
+              if (sub + c * LPN < D4) fold_max(best[c], arg[c], r[q][c], u[q]);
+          }
+        }
+      }
+    }
+    if (live) {
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) {
+        const int chunk = sub + c * LPN;
+        if (chunk < D4) {
+          float4 o = best[c];
+          if (arg[c].x < 0) o.x = 0.f;
+          if (arg[c].y < 0) o.y = 0.f;
+          if (arg[c].z < 0) o.z = 0.f;
+          if (arg[c].w < 0) o.w = 0.f;
+          stg_na(reinterpret_cast<float4*>(neigh + v * ldn) + chunk, o);
+          if (WRITE_ARG) stg_na(reinterpret_cast<int4*>(argmax + v * ldarg) + chunk, arg[c]);
+        }
+      }
+    }
+  }
+}
+
+// Scalar fallback: any D / alignment.  One warp per node, lanes stride over columns.
+__global__ void segmax_fwd_scalar_kernel(const float* __restrict__ P, int64_t ldp,
+                                         const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                         int32_t N, int32_t D, float* __restrict__ neigh, int64_t ldn,
+                                         int32_t* __restrict__ argmax, int64_t ldarg) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t v = warp_global; v < N; v += n_warps) {
+    const int32_t beg = indptr[v], end = indptr[v + 1];
+    for (int k = lane; k < D; k += 32) {
+      float best = -INFINITY;
+      int32_t a = -1;
+      for (int32_t p = beg; p < end; ++p) {
+        const int32_t u = indices[p];
+        const float x = P[(int64_t)u * ldp + k];
+        if (x > best) { best = x; a = u; }
+      }
+      neigh[v * ldn + k] = (a < 0) ? 0.f : best;
+      if (argmax) argmax[v * ldarg + k] = a;
+    }
+  }
+}
+
+// K2b (atomic form): one thread per float4 of dNeigh.
+__global__ void segmax_bwd_vec_kernel(const float* __restrict__ dN, int64_t ldd, const int32_t* __restrict__ arg,
+                                      int64_t ldarg, int64_t total4, int32_t D4, float* __restrict__ dP, int64_t lddp) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = i / D4;
+    const int c = (int)(i - v * D4);
+    const float4 g = ldg_nc_na(reinterpret_cast<const float4*>(dN + v * ldd) + c);
+    const int4 a = *(reinterpret_cast<const int4*>(arg + v * ldarg) + c);
+    const int k = c * 4;
+    if (a.x >= 0 && g.x != 0.f) atomicAdd(dP + (int64_t)a.x * lddp + k + 0, g.x);
+    if (a.y >= 0 && g.y != 0.f) atomicAdd(dP + (int64_t)a.y * lddp + k + 1, g.y);
+    if (a.z >= 0 && g.z != 0.f) atomicAdd(dP + (int64_t)a.z * lddp + k + 2, g.z);
+    if (a.w >= 0 && g.w != 0.f) atomicAdd(dP + (int64_t)a.w * lddp + k + 3, g.w);
+  }
+}
+
+__global__ void segmax_bwd_scalar_kernel(const float* __restrict__ dN, int64_t ldd, const int32_t* __restrict__ arg,
+                                         int64_t ldarg, int64_t N, int32_t D, float* __restrict__ dP, int64_t lddp) {
+  const int64_t total = N * D;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = i / D;
+    const int k = (int)(i - v * D);
+    const int32_t a = arg[v * ldarg + k];
+    const float g = dN[v * ldd + k];
+    if (a >= 0 && g != 0.f) atomicAdd(dP + (int64_t)a * lddp + k, g);
+  }
+}
+
+// K2b (deterministic form): one warp per SOURCE node, transposed gather over
+// the out-edge CSC; sums in CSC (edge id) order.
+__global__ void __launch_bounds__(kSegThreads)
+segmax_bwd_det_kernel(const float* __restrict__ dN, int64_t ldd, const int32_t* __restrict__ arg, int64_t ldarg,
+                      const int32_t* __restrict__ cptr, const int32_t* __restrict__ cidx, int32_t N, int32_t D,
+                      float* __restrict__ dP, int64_t lddp) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t u = warp_global; u < N; u += n_warps) {
+    const int32_t beg = cptr[u], end = cptr[u + 1];
+    for (int k = lane; k < D; k += 32) {
+      float acc = 0.f;
+      for (int32_t p = beg; p < end; ++p) {
+        const int32_t v = cidx[p];
+        if (arg[(int64_t)v * ldarg + k] == (int32_t)u) acc += dN[(int64_t)v * ldd + k];
+      }
+      dP[u * lddp + k] = acc;
+    }
+  }
+}
+
+// Sum-type aggregators (mean / gcn) — same traversal, additive fold.
+__global__ void __launch_bounds__(kSegThreads)
+segsum_fwd_kernel(const float* __restrict__ P, int64_t ldp, const int32_t* __restrict__ indptr,
+                  const int32_t* __restrict__ indices, int32_t N, int32_t D, int mode,
+                  float* __restrict__ out, int64_t ldo) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t v = warp_global; v < N; v += n_warps) {
+    const int32_t beg = indptr[v], end = indptr[v + 1];
+    const int32_t deg = end - beg;
+    for (int k = lane; k < D; k += 32) {
+      float acc = 0.f;
+      for (int32_t p = beg; p < end; ++p) acc += P[(int64_t)indices[p] * ldp + k];
+      if (mode == 1) acc = deg > 0 ? acc / (float)deg : 0.f;
+      else if (mode == 2) acc = (acc + P[v * ldp + k]) / (float)(deg + 1);
+      out[v * ldo + k] = acc;
+    }
+  }
+}
+
+
+__global__ void __launch_bounds__(kSegThreads)
+segsum_bwd_kernel(const float* __restrict__ dO, int64_t ldd, const int32_t* __restrict__ cptr,
+                  const int32_t* __restrict__ cidx, const int32_t* __restrict__ in_ptr, int32_t N, int32_t D, int mode,
+                  float* __restrict__ dP, int64_t lddp) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t u = warp_global; u < N; u += n_warps) {
+    const int32_t beg = cptr[u], end = cptr[u + 1];
+    for (int k = lane; k < D; k += 32) {
+      float acc = 0.f;
+      for (int32_t p = beg; p < end; ++p) {
+        const int32_t v = cidx[p];
+        const int32_t deg = in_ptr[v + 1] - in_ptr[v];
+        const float s = mode == 0 ? 1.f : (mode == 1 ? 1.f / (float)deg : 1.f / (float)(deg + 1));
+        acc = fmaf(s, dO[(int64_t)v * ldd + k], acc);
+      }
+      if (mode == 2) {
+        const int32_t deg = in_ptr[u + 1] - in_ptr[u];
+        acc += dO[u * ldd + k] / (float)(deg + 1);
+      }
+      dP[u * lddp + k] = acc;
+    }
+  }
+}
+
+__global__ void mask_pos_kernel(const float* __restrict__ g, const float* __restrict__ ref, int64_t n, float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = ref[i] > 0.f ? g[i] : 0.f;
+}
+
+static inline int seg_grid(int64_t warps_needed) {
+  const int wpb = kSegThreads / 32;
+  int64_t blocks = ceil_div<int64_t>(warps_needed, wpb);
+  const int64_t cap = (int64_t)sm_count() * 32;   // grid-stride beyond 32 resident-sized waves
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+template <int LPN, int VEC>
+static int launch_fwd_vec(const float* P, int64_t ldp, const int32_t* indptr, const int32_t* indices, int32_t N,
+                          int32_t D4, float* neigh, int64_t ldn, int32_t* argmax, int64_t ldarg, cudaStream_t st) {
+  const int64_t warps = ceil_div<int64_t>(N, 32 / LPN);
+  if (argmax)
+    segmax_fwd_vec_kernel<LPN, VEC, true><<<seg_grid(warps), kSegThreads, 0, st>>>(P, ldp, indptr, indices, N, D4, neigh, ldn, argmax, ldarg);
+  else
+    segmax_fwd_vec_kernel<LPN, VEC, false><<<seg_grid(warps), kSegThreads, 0, st>>>(P, ldp, indptr, indices, N, D4, neigh, ldn, nullptr, 0);
+  GTS_LAUNCH_CHECK();
+  return GTS_OK;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace gts
+
+using namespace gts;
+
+extern "C" {
+
+int gts_segmax_fwd(const float* P, int64_t ldp, const int32_t* indptr, const int32_t* indices,
+                   int32_t n_nodes, int32_t D, float* neigh, int64_t ldn,
+                   int32_t* argmax, int64_t ldarg, gts_stream_t stream) {
+  GTS_CHECK_ARG(n_nodes >= 0 && D >= 0, "gts_segmax_fwd: negative size");
+  if (n_nodes == 0 || D == 0) return GTS_OK;
+  GTS_CHECK_ARG(P && indptr && neigh, "gts_segmax_fwd: null pointer");
+  GTS_CHECK_ARG(ldp >= D && ldn >= D && (!argmax || ldarg >= D), "gts_segmax_fwd: leading dimension < D");
+  cudaStream_t st = as_stream(stream);
+  const bool vec_ok = (D % 4 == 0) && (ldp % 4 == 0) && (ldn % 4 == 0) && (!argmax || ldarg % 4 == 0) &&
+                      aligned16(P) && aligned16(neigh) && (!argmax || aligned16(argmax)) && D <= 1024;
+  if (vec_ok) {
+    const int D4 = D / 4;
+    if (D4 <= 4)   return launch_fwd_vec<4, 1>(P, ldp, indptr, indices, n_nodes, D4, neigh, ldn, argmax, ldarg, st);
+    if (D4 <= 8)   return launch_fwd_vec<8, 1>(P, ldp, indptr, indices, n_nodes, D4, neigh, ldn, argmax, ldarg, st);
+    if (D4 <= 16)  return launch_fwd_vec<16, 1>(P, ldp, indptr, indices, n_nodes, D4, neigh, ldn, argmax, ldarg, st);
+    if (D4 <= 32)  return launch_fwd_vec<32, 1>(P, ldp, indptr, indices, n_nodes, D4, neigh, ldn, argmax, ldarg, st);
+    if (D4 <= 64)  return launch_fwd_vec<32, 2>(P, ldp, indptr, indices, n_nodes, D4, neigh, ldn, argmax, ldarg, st);
+    if (D4 <= 128) return launch_fwd_vec<32, 4>(P, ldp, indptr, indices, n_nodes, D4, neigh, ldn, argmax, ldarg, st);
+    return launch_fwd_vec<32, 8>(P, ldp, indptr, indices, n_nodes, D4, neigh, ldn, argmax, ldarg, st);
+  }
+  segmax_fwd_scalar_kernel<<<seg_grid(n_nodes), kSegThreads, 0, st>>>(P, ldp, indptr, indices, n_nodes, D, neigh, ldn, argmax, ldarg);
+  GTS_LAUNCH_CHECK();
+  return GTS_OK;
+}
+
+int gts_segmax_bwd(const float* dNeigh, int64_t ldd, const int32_t* argmax, int64_t ldarg,
+                   int32_t n_nodes, int32_t D, float* dP, int64_t lddp, int32_t n_src_rows,
+                   gts_stream_t stream) {
+  GTS_CHECK_ARG(n_nodes >= 0 && D >= 0 && n_src_rows >= 0, "gts_segmax_bwd: negative size");
+  if (n_src_rows == 0 || D == 0) return GTS_OK;
+  GTS_CHECK_ARG(dP != nullptr, "gts_segmax_bwd: dP is null");
+  GTS_CHECK_ARG(lddp >= D, "gts_segmax_bwd: lddp < D");
+  cudaStream_t st = as_stream(stream);
+  if (lddp == D) {
+    GTS_CUDA(cudaMemsetAsync(dP, 0, sizeof(float) * (size_t)n_src_rows * D, st));
+  } else {
+    GTS_CUDA(cudaMemset2DAsync(dP, sizeof(float) * lddp, 0, sizeof(float) * D, n_src_rows, st));
+  }
+  if (n_nodes == 0) return GTS_OK;
+  GTS_CHECK_ARG(dNeigh && argmax, "gts_segmax_bwd: null pointer");
+  const bool vec_ok = (D % 4 == 0) && (ldd % 4 == 0) && (ldarg % 4 == 0) && aligned16(dNeigh) && aligned16(argmax);
+  const int threads = 256;
+  if (vec_ok) {
+    const int64_t total4 = (int64_t)n_nodes * (D / 4);
+    int64_t blocks = ceil_div<int64_t>(total4, threads);
+    const int64_t cap = (int64_t)sm_count() * 64;
+    if (blocks > cap) blocks = cap;
+    segmax_bwd_vec_kernel<<<(int)blocks, threads, 0, st>>>(dNeigh, ldd, argmax, ldarg, total4, D / 4, dP, lddp);
+  } else {
+    const int64_t total = (int64_t)n_nodes * D;
+    int64_t blocks = ceil_div<int64_t>(total, threads);
+    const int64_t cap = (int64_t)sm_count() * 64;
+    if (blocks > cap) blocks = cap;
+    segmax_bwd_scalar_kernel<<<(int)blocks, threads, 0, st>>>(dNeigh, ldd, argmax, ldarg, n_nodes, D, dP, lddp);
+  }
+  GTS_LAUNCH_CHECK();
+  return GTS_OK;
+}
+
+int gts_segmax_bwd_det(const float* dNeigh, int64_t ldd, const int32_t* argmax, int64_t ldarg,
+                       const int32_t* csc_indptr, const int32_t* csc_indices,
+                       int32_t n_nodes, int32_t D, float* dP, int64_t lddp, gts_stream_t stream) {
+  GTS_CHECK_ARG(n_nodes >= 0 && D >= 0, "gts_segmax_bwd_det: negative size");
+  if (n_nodes == 0 || D == 0) return GTS_OK;
+  GTS_CHECK_ARG(dNeigh && argmax && csc_indptr && dP, "gts_segmax_bwd_det: null pointer");
+  segmax_bwd_det_kernel<<<seg_grid(n_nodes), kSegThreads, 0, as_stream(stream)>>>(dNeigh, ldd, argmax, ldarg, csc_indptr,
+                                                                                   csc_indices, n_nodes, D, dP, lddp);
+  GTS_LAUNCH_CHECK();
+  return GTS_OK;
+}
+
+int gts_segsum_fwd(const float* P, int64_t ldp, const int32_t* indptr, const int32_t* indices,
+                   int32_t n_nodes, int32_t D, int32_t mode, float* out, int64_t ldo, gts_stream_t stream) {
+  GTS_CHECK_ARG(n_nodes >= 0 && D >= 0, "gts_segsum_fwd: negative size");
+  GTS_CHECK_ARG(mode >= 0 && mode <= 2, "gts_segsum_fwd: mode must be 0 (sum), 1 (mean) or 2 (gcn)");
+  if (n_nodes == 0 || D == 0) return GTS_OK;
+  GTS_CHECK_ARG(P && indptr && out, "gts_segsum_fwd: null pointer");
+  segsum_fwd_kernel<<<seg_grid(n_nodes), kSegThreads, 0, as_stream(stream)>>>(P, ldp, indptr, indices, n_nodes, D, mode, out, ldo);
+  GTS_LAUNCH_CHECK();
+  return GTS_OK;
+}
+
+int gts_segsum_bwd(const float* dOut, int64_t ldd, const int32_t* csc_indptr, const int32_t* csc_indices,
+                   const int32_t* in_indptr, int32_t n_nodes, int32_t D, int32_t mode,
+                   float* dP, int64_t lddp, gts_stream_t stream) {
+  GTS_CHECK_ARG(n_nodes >= 0 && D >= 0, "gts_segsum_bwd: negative size");
+  GTS_CHECK_ARG(mode >= 0 && mode <= 2, "gts_segsum_bwd: mode must be 0, 1 or 2");
+  if (n_nodes == 0 || D == 0) return GTS_OK;
+  GTS_CHECK_ARG(dOut && csc_indptr && in_indptr && dP, "gts_segsum_bwd: null pointer");
+  segsum_bwd_kernel<<<seg_grid(n_nodes), kSegThreads, 0, as_stream(stream)>>>(dOut, ldd, csc_indptr, csc_indices, in_indptr,
+                                                                               n_nodes, D, mode, dP, lddp);
+  GTS_LAUNCH_CHECK();
+  return GTS_OK;
+}
+
+int gts_mask_pos(const float* grad, const float* ref, int64_t n, float* out, gts_stream_t stream) {
+  GTS_CHECK_ARG(n >= 0, "gts_mask_pos: negative size");
+  if (n == 0) return GTS_OK;
+  GTS_CHECK_ARG(grad && ref && out, "gts_mask_pos: null pointer");
+  int64_t b = ceil_div<int64_t>(n, 256);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (b > cap) b = cap;
+  mask_pos_kernel<<<(int)b, 256, 0, as_stream(stream)>>>(grad, ref, n, out);
+  GTS_LAUNCH_CHECK();
+  return GTS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+"""Training / evaluation wrapper with the reference's entry points
+(model/gnn_model.py:21-90): ``GNN(model_type, hyperparameters, train_dataset)``
+with ``.net .optimizer .lr_decay .loss_fcn .train_loader .device``,
+``run_epoch()``, ``evaluate(dataset)``, ``save_weights(folder, name)``.
+
+The dataset contract is the reference's ImageGraphDataset one: iterating yields
+``(mri_id, graph, features, labels)`` where ``graph`` is a host
+``BatchedGraph`` (gnn_tumor_seg_b200.graph) instead of a DGLGraph.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader
+
+from . import ops
+from ._lib import GtsError
+from .graph import minibatch_graphs
+from .networks import init_graph_net
+from .project import project_nodes_to_img
+
+BATCH_SIZE = 6          # model/gnn_model.py:12
+
+
+class WeightedCrossEntropy(torch.nn.Module):
+    """torch.nn.CrossEntropyLoss(weight=w) computed by the fused K8 kernel."""
+
+    def __init__(self, weight):
+        super().__init__()
+        self.register_buffer("weight", weight)
+
+    def forward(self, logits, labels):
+        return ops.weighted_cross_entropy(logits, labels, self.weight)
+
+
+def _dice(pred, true, cls):
+    p, t = pred == cls, true == cls
+    denom = p.sum() + t.sum()
+    return float(2.0 * (p & t).sum() / denom) if denom > 0 else float("nan")
+
+
+class GNN:
+    def __init__(self, model_type, hyperparameters, train_dataset):
+        if not torch.cuda.is_available():
+            raise GtsError("gnn_tumor_seg_b200.GNN needs a CUDA device (B200); there is no CPU path")
+        self.device = torch.device('cuda')
+        print("Using device", self.device)
+        class_weights = torch.FloatTensor(hyperparameters.class_weights).to(self.device)
+        self.net = init_graph_net(model_type, hyperparameters)
+        self.net.to(self.device)
+        self.optimizer = torch.optim.AdamW(self.net.parameters(), lr=hyperparameters.lr,
+                                           weight_decay=hyperparameters.w_decay)
+        self.lr_decay = torch.optim.lr_scheduler.ExponentialLR(self.optimizer, hyperparameters.lr_decay, last_epoch=-1)
+        self.loss_fcn = WeightedCrossEntropy(class_weights)
+        self.train_loader = DataLoader(train_dataset, batch_size=BATCH_SIZE, shuffle=True, num_workers=0,
+                                       collate_fn=minibatch_graphs) if train_dataset is not None else None
+
+    def run_epoch(self):
+        self.net.train()
+        losses = []
+        for batch_mris, batch_graphs, batch_features, batch_labels in self.train_loader:
+            batch_graphs = batch_graphs.to(self.device)
+            batch_features = batch_features.to(self.device)
+            batch_labels = batch_labels.to(self.device)
+            logits = self.net(batch_graphs, batch_features)
+            loss = self.loss_fcn(logits, batch_labels)
+            losses.append(loss.detach())          # read back once per epoch, not per step
+            self.optimizer.zero_grad()
+            loss.backward()
+            self.optimizer.step()
+        self.lr_decay.step()
+        return float(torch.stack(losses).mean().item()) if losses else float("nan")
+
+    # must be a Subset of an ImageGraphDataset (or any object with the same protocol)
+    def evaluate(self, dataset):
+        base = getattr(dataset, "dataset", dataset)
+        assert getattr(base, "read_label", True) == True
+        self.net.eval()
+        # metrics: loss, 3 node dices, 3 voxel dices, 3 voxel hausdorff (HD95 is out of scope -> nan)
+        metrics = np.zeros((len(dataset), 10))
+        counts = np.zeros((len(dataset), 8))
+        i = 0
+        for curr_id, curr_graph, curr_feats, curr_labels in dataset:
+            curr_graph = curr_graph.to(self.device)
+            curr_feats = torch.FloatTensor(curr_feats).to(self.device)
+            curr_labels = torch.LongTensor(curr_labels).to(self.device)
+            with torch.no_grad():
+                logits = self.net(curr_graph, curr_feats)
+                loss = self.loss_fcn(logits, curr_labels)
+            _, predicted_classes = torch.max(logits, dim=1)
+            predicted_classes = predicted_classes.detach().cpu().numpy()
+            metrics[i][0] = loss.item()
+            ct, res = self.calculate_all_metrics_for_brain(curr_id, dataset, predicted_classes,
+                                                           curr_labels.detach().cpu().numpy())
+            metrics[i][1:] = res
+            counts[i] = ct
+            i += 1
+        avg_metrics = np.mean(metrics, axis=0)
+        total_counts = np.sum(counts, axis=0)
+        return avg_metrics, total_counts
+
+    def calculate_all_metrics_for_brain(self, mri_id, dataset, node_preds, node_labels):
+        label_counts = np.concatenate([np.bincount(node_preds, minlength=4)[:4], np.bincount(node_labels, minlength=4)[:4]])
+        # BraTS regions on the reference's internal labels: WT = !=0, TC = {2,3}... kept simple: per-class Dice 1..3
+        node_dices = np.array([_dice(node_preds, node_labels, c) for c in (1, 2, 3)])
+        voxel_metrics = np.full(6, np.nan)
+        base = getattr(dataset, "dataset", dataset)
+        if hasattr(base, "get_supervoxel_partitioning") and hasattr(base, "get_voxel_labels"):
+            sv_partitioning = base.get_supervoxel_partitioning(mri_id)
+            true_voxels = base.get_voxel_labels(mri_id)
+            pred_voxels = project_nodes_to_img(sv_partitioning, node_preds)
+            voxel_metrics[:3] = [_dice(pred_voxels, true_voxels, c) for c in (1, 2, 3)]
+        return label_counts, np.concatenate([node_dices, voxel_metrics])
+
+    def save_weights(self, folder, name):
+        torch.save(self.net.state_dict(), f"{folder}{name}.pt")

@@ -1,0 +1,528 @@
+"""Tensor-level wrappers over the C-ABI (include/gts.h) and the autograd
+Functions built from them.
+
+PyTorch is plumbing here: it owns device memory (outputs, workspaces), the
+current stream, and the autograd tape; all arithmetic on the hot path runs in
+libgts.so kernels.  Every wrapper requires CUDA tensors and raises otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib
+from ._lib import ACT_MASK_POS, ACT_NONE, ACT_RELU, GEMM_MODES, GemmNtArgs, check, ptr, require_cuda, stream_ptr
+
+# ---------------------------------------------------------------------------
+# arithmetic mode of the dense contractions (stated per run in bench/tests)
+# ---------------------------------------------------------------------------
+_gemm_mode = GEMM_MODES[os.environ.get("GTS_GEMM_MODE", "tf32x3")]
+
+
+def set_gemm_mode(mode: str) -> None:
+    """'fp32' (SIMT FFMA), 'tf32' (tcgen05 1xTF32) or 'tf32x3' (tcgen05 3xTF32)."""
+    global _gemm_mode
+    _gemm_mode = GEMM_MODES[mode]
+
+
+def get_gemm_mode() -> str:
+    return {v: k for k, v in GEMM_MODES.items()}[_gemm_mode]
+
+
+_deterministic = os.environ.get("GTS_DETERMINISTIC", "0") == "1"
+
+
+def set_deterministic_backward(flag: bool) -> None:
+    """True: neighbour-max backward uses the transposed gather over the out-edge
+    CSC (no float atomics, bit-reproducible); False: atomic scatter (faster)."""
+    global _deterministic
+    _deterministic = bool(flag)
+
+
+def deterministic_backward() -> bool:
+    return _deterministic
+
+
+# counts kernels launched through this module (bench.py's gpu_launches claim)
+launch_counter = {"n": 0}
+
+
+def _count(n: int = 1) -> None:
+    launch_counter["n"] += n
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _row_major_2d(t: torch.Tensor) -> torch.Tensor:
+    """fp32 2-D with unit column stride (row stride arbitrary >= cols)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.dim() != 2:
+        raise ValueError(f"expected a 2-D tensor, got shape {tuple(t.shape)}")
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        t = t.contiguous()
+    if t.shape[0] > 1 and t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t
+
+
+def _ld(t: torch.Tensor) -> int:
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ---------------------------------------------------------------------------
+# K6 graph build
+# ---------------------------------------------------------------------------
+def batch_edges(src_local, dst_local, edge_off, node_off):
+    require_cuda(src_local, dst_local, edge_off, node_off)
+    lib = _lib.load()
+    E = src_local.numel()
+    src_g = torch.empty(E, dtype=torch.int32, device=src_local.device)
+    dst_g = torch.empty(E, dtype=torch.int32, device=src_local.device)
+    check(lib.gts_batch_edges(ptr(src_local), ptr(dst_local), E, ptr(edge_off), ptr(node_off),
+                              edge_off.numel() - 1, ptr(src_g), ptr(dst_g), stream_ptr()), "gts_batch_edges")
+    _count()
+    return src_g, dst_g
+
+
+def csr_build(row, col, n_nodes, want_eid=False):
+    """Canonical CSR keyed by `row` (int32 CUDA tensors)."""
+    require_cuda(row, col)
+    lib = _lib.load()
+    E = row.numel()
+    dev = row.device
+    indptr = torch.empty(n_nodes + 1, dtype=torch.int32, device=dev)
+    indices = torch.empty(E, dtype=torch.int32, device=dev)
+    eid = torch.empty(E, dtype=torch.int32, device=dev) if want_eid else None
+    ws = _workspace(lib.gts_csr_build_workspace_bytes(E, n_nodes), dev)
+    check(lib.gts_csr_build(ptr(row), ptr(col), E, n_nodes, ptr(indptr), ptr(indices), ptr(eid),
+                            ptr(ws), ws.numel(), stream_ptr()), "gts_csr_build")
+    _count(7)
+    return indptr, indices, eid
+
+
+def edge_perm_compose(eid_csr, eid_csc):
+    require_cuda(eid_csr, eid_csc)
+    lib = _lib.load()
+    E = eid_csr.numel()
+    scratch = torch.empty(E, dtype=torch.int32, device=eid_csr.device)
+    out = torch.empty(E, dtype=torch.int32, device=eid_csr.device)
+    check(lib.gts_edge_perm_compose(ptr(eid_csr), ptr(eid_csc), E, ptr(scratch), ptr(out), stream_ptr()),
+          "gts_edge_perm_compose")
+    _count(2)
+    return out
+
+
+# ---------------------------------------------------------------------------
+# dense contractions
+# ---------------------------------------------------------------------------
+def gemm_nt(A1, B1, A2=None, B2=None, bias=None, act=ACT_NONE, aux=None, mode=None, out=None):
+    """act(A1 @ B1.T + A2 @ B2.T + bias); B* in nn.Linear layout [out,in]."""
+    require_cuda(A1, B1, A2, B2, bias, aux)
+    lib = _lib.load()
+    A1 = _row_major_2d(A1)
+    B1 = _row_major_2d(B1)
+    M, K1 = A1.shape
+    N = B1.shape[0]
+    assert B1.shape[1] == K1, (A1.shape, B1.shape)
+    a = GemmNtArgs()
+    a.A1, a.lda1, a.K1 = ptr(A1), _ld(A1), K1
+    a.B1, a.ldb1 = ptr(B1), _ld(B1)
+    if A2 is not None:
+        A2 = _row_major_2d(A2)
+        B2 = _row_major_2d(B2)
+        assert A2.shape[0] == M and B2.shape[0] == N and A2.shape[1] == B2.shape[1]
+        a.A2, a.lda2, a.K2 = ptr(A2), _ld(A2), A2.shape[1]
+        a.B2, a.ldb2 = ptr(B2), _ld(B2)
+    else:
+        a.A2, a.lda2, a.K2, a.B2, a.ldb2 = None, 0, 0, None, 0
+    if bias is not None:
+        bias = _f32c(bias)
+        assert bias.numel() == N
+    a.bias = ptr(bias)
+    if aux is not None:
+        aux = _row_major_2d(aux)
+        assert tuple(aux.shape) == (M, N)
+        a.aux, a.ldaux = ptr(aux), _ld(aux)
+    else:
+        a.aux, a.ldaux = None, 0
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A1.device)
+    a.C, a.ldc = ptr(out), _ld(out)
+    a.M, a.N, a.act = M, N, act
+    a.mode = _gemm_mode if mode is None else (GEMM_MODES[mode] if isinstance(mode, str) else mode)
+    check(lib.gts_gemm_nt(C.byref(a), stream_ptr()), "gts_gemm_nt")
+    _count()
+    return out
+
+
+def gemm_tn(A, B, mode=None):
+    """A.T @ B for A [K,Mo], B [K,No] (weight gradients)."""
+    require_cuda(A, B)
+    lib = _lib.load()
+    A = _row_major_2d(A)
+    B = _row_major_2d(B)
+    K, Mo = A.shape
+    No = B.shape[1]
+    assert B.shape[0] == K
+    m = _gemm_mode if mode is None else (GEMM_MODES[mode] if isinstance(mode, str) else mode)
+    out = torch.empty((Mo, No), dtype=torch.float32, device=A.device)
+    ws = _workspace(lib.gts_gemm_tn_workspace_bytes(Mo, No, K, m), A.device)
+    check(lib.gts_gemm_tn(ptr(A), _ld(A), ptr(B), _ld(B), ptr(out), No, Mo, No, K, m, ptr(ws), ws.numel(),
+                          stream_ptr()), "gts_gemm_tn")
+    _count(2)
+    return out
+
+
+def colsum(A):
+    require_cuda(A)
+    lib = _lib.load()
+    A = _row_major_2d(A)
+    rows, cols = A.shape
+    out = torch.empty(cols, dtype=torch.float32, device=A.device)
+    ws = _workspace(lib.gts_colsum_workspace_bytes(rows, cols), A.device)
+    check(lib.gts_colsum(ptr(A), _ld(A), rows, cols, ptr(out), ptr(ws), ws.numel(), stream_ptr()), "gts_colsum")
+    _count(2)
+    return out
+
+
+def transpose(W):
+    require_cuda(W)
+    lib = _lib.load()
+    W = _row_major_2d(W)
+    r, c = W.shape
+    out = torch.empty((c, r), dtype=torch.float32, device=W.device)
+    check(lib.gts_transpose(ptr(W), _ld(W), r, c, ptr(out), r, stream_ptr()), "gts_transpose")
+    _count()
+    return out
+
+
+def mask_pos(grad, ref):
+    require_cuda(grad, ref)
+    lib = _lib.load()
+    grad = _f32c(grad)
+    ref = _f32c(ref)
+    out = torch.empty_like(grad)
+    check(lib.gts_mask_pos(ptr(grad), ptr(ref), grad.numel(), ptr(out), stream_ptr()), "gts_mask_pos")
+    _count()
+    return out
+
+
+# ---------------------------------------------------------------------------
+# K2 aggregation
+# ---------------------------------------------------------------------------
+def segmax_fwd(P, indptr, indices, want_argmax=True):
+    require_cuda(P, indptr, indices)
+    lib = _lib.load()
+    P = _row_major_2d(P)
+    N = indptr.numel() - 1
+    D = P.shape[1]
+    neigh = torch.empty((N, D), dtype=torch.float32, device=P.device)
+    arg = torch.empty((N, D), dtype=torch.int32, device=P.device) if want_argmax else None
+    check(lib.gts_segmax_fwd(ptr(P), _ld(P), ptr(indptr), ptr(indices), N, D, ptr(neigh), D,
+                             ptr(arg), D, stream_ptr()), "gts_segmax_fwd")
+    _count()
+    return neigh, arg
+
+
+def segmax_bwd(dNeigh, arg, n_src_rows, csc=None):
+    """Scatter through the saved arg-max.  ``csc=(indptr, indices)`` selects the
+    deterministic transposed-gather form."""
+    require_cuda(dNeigh, arg)
+    lib = _lib.load()
+    dNeigh = _row_major_2d(dNeigh)
+    N, D = dNeigh.shape
+    dP = torch.empty((n_src_rows, D), dtype=torch.float32, device=dNeigh.device)
+    if csc is None:
+        check(lib.gts_segmax_bwd(ptr(dNeigh), _ld(dNeigh), ptr(arg), D, N, D, ptr(dP), D, n_src_rows,
+                                 stream_ptr()), "gts_segmax_bwd")
+        _count(2)
+    else:
+        assert n_src_rows == N
+        check(lib.gts_segmax_bwd_det(ptr(dNeigh), _ld(dNeigh), ptr(arg), D, ptr(csc[0]), ptr(csc[1]), N, D,
+                                     ptr(dP), D, stream_ptr()), "gts_segmax_bwd_det")
+        _count()
+    return dP
+
+
+SEGSUM_MODES = {"sum": 0, "mean": 1, "gcn": 2}
+
+
+def segsum_fwd(P, indptr, indices, mode):
+    require_cuda(P, indptr, indices)
+    lib = _lib.load()
+    P = _row_major_2d(P)
+    N = indptr.numel() - 1
+    D = P.shape[1]
+    out = torch.empty((N, D), dtype=torch.float32, device=P.device)
+    check(lib.gts_segsum_fwd(ptr(P), _ld(P), ptr(indptr), ptr(indices), N, D, SEGSUM_MODES[mode], ptr(out), D,
+                             stream_ptr()), "gts_segsum_fwd")
+    _count()
+    return out
+
+
+def segsum_bwd(dOut, csc_indptr, csc_indices, in_indptr, mode):
+    require_cuda(dOut, csc_indptr, csc_indices, in_indptr)
+    lib = _lib.load()
+    dOut = _row_major_2d(dOut)
+    N, D = dOut.shape
+    dP = torch.empty((N, D), dtype=torch.float32, device=dOut.device)
+    check(lib.gts_segsum_bwd(ptr(dOut), _ld(dOut), ptr(csc_indptr), ptr(csc_indices), ptr(in_indptr), N, D,
+                             SEGSUM_MODES[mode], ptr(dP), D, stream_ptr()), "gts_segsum_bwd")
+    _count()
+    return dP
+
+
+# ---------------------------------------------------------------------------
+# K8 loss
+# ---------------------------------------------------------------------------
+def ce_weighted(logits, labels, class_w, want_grad=True):
+    """Returns (sums[2] = [sum w*nll, sum w], dlogits_unnormalised | None)."""
+    require_cuda(logits, labels, class_w)
+    lib = _lib.load()
+    logits = _row_major_2d(logits)
+    labels = labels.contiguous()
+    if labels.dtype != torch.int64:
+        labels = labels.long()
+    class_w = _f32c(class_w)
+    N, Cn = logits.shape
+    sums = torch.zeros(2, dtype=torch.float32, device=logits.device)
+    dl = torch.empty((N, Cn), dtype=torch.float32, device=logits.device) if want_grad else None
+    check(lib.gts_ce_weighted(ptr(logits), _ld(logits), ptr(labels), ptr(class_w), N, Cn, ptr(sums), ptr(dl), Cn,
+                              stream_ptr()), "gts_ce_weighted")
+    _count()
+    return sums, dl
+
+
+def scale_by_inv_(x, alpha, denom):
+    require_cuda(x, denom)
+    lib = _lib.load()
+    assert x.is_contiguous() and x.dtype == torch.float32
+    check(lib.gts_scale_by_inv(ptr(x), x.numel(), float(alpha), ptr(denom), stream_ptr()), "gts_scale_by_inv")
+    _count()
+    return x
+
+
+class _WeightedCE(torch.autograd.Function):
+    """Weighted-mean CE as one fused kernel (+ one scale): drop-in for
+    torch.nn.CrossEntropyLoss(weight=w)(logits, labels) (model/gnn_model.py:30,42)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, class_w):
+        sums, dl = ce_weighted(logits, labels, class_w, want_grad=True)
+        scale_by_inv_(dl, 1.0, sums[1:2])
+        ctx.save_for_backward(dl)
+        return sums[0] / sums[1]
+
+    @staticmethod
+    def backward(ctx, g):
+        (dl,) = ctx.saved_tensors
+        return dl * g, None, None
+
+
+def weighted_cross_entropy(logits, labels, class_w):
+    return _WeightedCE.apply(logits, labels, class_w)
+
+
+# ---------------------------------------------------------------------------
+# SAGEConv('pool') layer: forward + backward as kernel sequences
+# ---------------------------------------------------------------------------
+class SagePoolLayerFn(torch.autograd.Function):
+    """One DGL SAGEConv(in,out,'pool') layer.
+
+    forward : P = relu(h Wp^T + bp) -> (neigh, arg) = segmax(P) ->
+              out = act(h Ws^T + neigh Wn^T + b)          [3 kernels]
+    backward: see _backward below.
+
+    ``input_is_relu``: h is the ReLU output of the previous layer, so the
+    gradient returned for h may be pre-masked by (h > 0) inside the GEMM
+    epilogue; ``grad_premasked``: the incoming gradient already carries this
+    layer's own ReLU mask (the consumer pre-masked it).  Both are set only by
+    GraphSage.forward for its strictly sequential stack.
+    """
+
+    @staticmethod
+    def forward(ctx, h, Wp, bp, Ws, Wn, b, graph, relu_out, input_is_relu, grad_premasked, deterministic):
+        require_cuda(h, Wp, bp, Ws, Wn, b)
+        h = _row_major_2d(h)
+        indptr, indices = graph.csr
+        P = gemm_nt(h, Wp, bias=bp, act=ACT_RELU)
+        need_grad = any(ctx.needs_input_grad[:6])
+        neigh, arg = segmax_fwd(P, indptr, indices, want_argmax=need_grad)
+        del P
+        out = gemm_nt(h, Ws, neigh, Wn, bias=b, act=ACT_RELU if relu_out else ACT_NONE)
+        if need_grad:
+            ctx.save_for_backward(h, neigh, arg, out if relu_out else None, Wp, Ws, Wn)
+            ctx.graph = graph
+            ctx.flags = (relu_out, input_is_relu, grad_premasked, deterministic)
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        h, neigh, arg, out, Wp, Ws, Wn = ctx.saved_tensors
+        relu_out, input_is_relu, grad_premasked, deterministic = ctx.flags
+        dOut = _row_major_2d(dOut)
+        dZ = mask_pos(dOut, out) if (relu_out and not grad_premasked) else dOut
+        db = colsum(dZ)
+        dWs = gemm_tn(dZ, h)
+        dWn = gemm_tn(dZ, neigh)
+        # dNeigh' = (dZ Wn) * (neigh > 0): ReLU mask of fc_pool folded here, since
+        # neigh[v,k] = P[arg[v,k],k] (Appendix A.1)
+        dNeigh = gemm_nt(dZ, transpose(Wn), act=ACT_MASK_POS, aux=neigh)
+        csc = ctx.graph.csc[:2] if deterministic else None
+        dP = segmax_bwd(dNeigh, arg, h.shape[0], csc=csc)
+        del dNeigh
+        dWp = gemm_tn(dP, h)
+        dbp = colsum(dP)
+        dh = None
+        if ctx.needs_input_grad[0]:
+            dh = gemm_nt(dZ, transpose(Ws), dP, transpose(Wp),
+                         act=ACT_MASK_POS if input_is_relu else ACT_NONE, aux=h if input_is_relu else None)
+        return dh, dWp, dbp, dWs, dWn, db, None, None, None, None, None
+
+
+def sage_pool_layer(h, Wp, bp, Ws, Wn, b, graph, relu_out, input_is_relu=False, grad_premasked=False,
+                    deterministic=False):
+    return SagePoolLayerFn.apply(h, Wp, bp, Ws, Wn, b, graph, relu_out, input_is_relu, grad_premasked, deterministic)
+
+
+class SageSumLayerFn(torch.autograd.Function):
+    """SAGEConv 'mean' / 'gcn' (reference model/networks.py:72-75).
+
+    mean: out = act(h Ws^T + mean_in(h) Wn^T + b);  gcn: out = act(((sum_in(h)+h)/(deg+1)) Wn^T + b)
+    (DGL applies fc_neigh before aggregating when in > out; the result is the
+    same up to fp32 rounding because the aggregation is linear).
+    """
+
+    @staticmethod
+    def forward(ctx, h, Ws, Wn, b, graph, agg, relu_out):
+        require_cuda(h, Wn, b)
+        h = _row_major_2d(h)
+        indptr, indices = graph.csr
+        neigh = segsum_fwd(h, indptr, indices, agg)
+        act = ACT_RELU if relu_out else ACT_NONE
+        if agg == "gcn":
+            out = gemm_nt(neigh, Wn, bias=b, act=act)
+        else:
+            out = gemm_nt(h, Ws, neigh, Wn, bias=b, act=act)
+        ctx.save_for_backward(h, neigh, out if relu_out else None, Ws, Wn)
+        ctx.graph, ctx.agg, ctx.relu_out = graph, agg, relu_out
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        h, neigh, out, Ws, Wn = ctx.saved_tensors
+        graph, agg = ctx.graph, ctx.agg
+        dZ = mask_pos(dOut, out) if ctx.relu_out else _row_major_2d(dOut)
+        db = colsum(dZ)
+        dWn = gemm_tn(dZ, neigh)
+        dNeigh = gemm_nt(dZ, transpose(Wn))
+        cptr, cidx, _ = graph.csc
+        dh = segsum_bwd(dNeigh, cptr, cidx, graph.csr[0], agg)
+        dWs = None
+        if agg != "gcn":
+            dWs = gemm_tn(dZ, h)
+            dh = dh + gemm_nt(dZ, transpose(Ws))
+        return dh, dWs, dWn, db, None, None, None
+
+
+# ---------------------------------------------------------------------------
+# GATConv layer
+# ---------------------------------------------------------------------------
+class GatLayerFn(torch.autograd.Function):
+    """One DGL GATConv layer: fc GEMM -> scores ->
+    fused edge-softmax aggregation (+residual +bias +ELU); backward = two
+    deterministic edge passes + GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, W, attn_l, attn_r, bias, Wres, graph, H, F, slope, residual_identity, elu):
+        require_cuda(x, W, attn_l, attn_r)
+        lib = _lib.load()
+        x = _row_major_2d(x)
+        N = x.shape[0]
+        dev = x.device
+        indptr, indices = graph.csr
+        Z = gemm_nt(x, W)                                   # [N, H*F]
+        al = _f32c(attn_l).view(H, F)
+        ar = _f32c(attn_r).view(H, F)
+        el = torch.empty((N, H), dtype=torch.float32, device=dev)
+        er = torch.empty((N, H), dtype=torch.float32, device=dev)
+        st = stream_ptr()
+        check(lib.gts_gat_scores(ptr(Z), H * F, ptr(al), ptr(ar), N, H, F, ptr(el), ptr(er), st), "gts_gat_scores")
+        res = None
+        if Wres is not None:
+            res = gemm_nt(x, Wres)
+        elif residual_identity:
+            res = x
+        out = torch.empty((N, H * F), dtype=torch.float32, device=dev)
+        rowmax = torch.empty((N, H), dtype=torch.float32, device=dev)
+        rowsum = torch.empty((N, H), dtype=torch.float32, device=dev)
+        err = graph.err_flag
+        bias_c = _f32c(bias) if bias is not None else None
+        check(lib.gts_gat_fwd(ptr(Z), H * F, ptr(el), ptr(er), ptr(indptr), ptr(indices), N, H, F, float(slope),
+                              ptr(res), (_ld(res) if res is not None else 0), ptr(bias_c), 1 if elu else 0,
+                              ptr(out), H * F, ptr(rowmax), ptr(rowsum), ptr(err), st), "gts_gat_fwd")
+        _count(2)
+        ctx.save_for_backward(x, W, al, ar, Wres, Z, el, er, rowmax, rowsum, out if elu else None)
+        ctx.graph = graph
+        ctx.cfg = (H, F, float(slope), residual_identity, elu, bias is not None)
+        return out.view(N, H, F)
+
+    @staticmethod
+    def backward(ctx, dOut):
+        lib = _lib.load()
+        x, W, al, ar, Wres, Z, el, er, rowmax, rowsum, out = ctx.saved_tensors
+        H, F, slope, residual_identity, elu, has_bias = ctx.cfg
+        graph = ctx.graph
+        N = x.shape[0]
+        dev = x.device
+        st = stream_ptr()
+        dOut = _f32c(dOut).view(N, H * F)
+        if elu:
+            dR = torch.empty_like(dOut)
+            check(lib.gts_gat_act_bwd(ptr(dOut), ptr(out), dOut.numel(), 1, ptr(dR), st), "gts_gat_act_bwd")
+            _count()
+        else:
+            dR = dOut
+        indptr, indices = graph.csr
+        cptr, cidx, c2r = graph.csc
+        E = indices.numel()
+        dt = torch.empty((E, H), dtype=torch.float32, device=dev)
+        der = torch.empty((N, H), dtype=torch.float32, device=dev)
+        check(lib.gts_gat_bwd_dst(ptr(Z), H * F, ptr(el), ptr(er), ptr(rowmax), ptr(rowsum), ptr(indptr), ptr(indices),
+                                  ptr(dR), H * F, N, H, F, slope, ptr(dt), ptr(der), st), "gts_gat_bwd_dst")
+        dZ = torch.empty((N, H * F), dtype=torch.float32, device=dev)
+        del_ = torch.empty((N, H), dtype=torch.float32, device=dev)
+        check(lib.gts_gat_bwd_src(ptr(el), ptr(er), ptr(rowmax), ptr(rowsum), ptr(cptr), ptr(cidx), ptr(c2r),
+                                  ptr(dR), H * F, ptr(dt), ptr(der), ptr(al), ptr(ar), N, H, F, slope,
+                                  ptr(dZ), H * F, ptr(del_), st), "gts_gat_bwd_src")
+        ws = _workspace(lib.gts_gat_attn_grad_workspace_bytes(N, H, F), dev)
+        dal = torch.empty((1, H, F), dtype=torch.float32, device=dev)
+        dar = torch.empty((1, H, F), dtype=torch.float32, device=dev)
+        check(lib.gts_gat_attn_grad(ptr(Z), H * F, ptr(del_), N, H, F, ptr(dal), ptr(ws), ws.numel(), st),
+              "gts_gat_attn_grad")
+        check(lib.gts_gat_attn_grad(ptr(Z), H * F, ptr(der), N, H, F, ptr(dar), ptr(ws), ws.numel(), st),
+              "gts_gat_attn_grad")
+        _count(6)
+        dW = gemm_tn(dZ, x)
+        dbias = colsum(dR) if has_bias else None
+        dWres = gemm_tn(dR, x) if Wres is not None else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if Wres is not None:
+                dx = gemm_nt(dZ, transpose(W), dR, transpose(Wres))
+            else:
+                dx = gemm_nt(dZ, transpose(W))
+                if residual_identity:
+                    dx = dx + dR
+        return dx, dW, dal, dar, dbias, dWres, None, None, None, None, None, None

@@ -1,0 +1,290 @@
+/*
+ * gts.h — C-ABI of libgts.so, the B200 (sm_100a) message-passing hot path of
+ * GNN-Tumor-Seg (reference: rsinghlab/GNN-Tumor-Seg, /root/reference).
+ *
+ * The reference has no FFI of its own: its hot path runs inside DGL
+ * (SAGEConv / GATConv / dgl.batch) and numpy.  Each entry point below names
+ * the reference call site (file:line under /root/reference) whose arithmetic
+ * it replaces; INTEGRATION.md shows the ctypes binding a maintainer of the
+ * reference would add.
+ *
+ * Conventions (every function):
+ *   - returns 0 (GTS_OK) or a gts_status error code; gts_last_error() returns
+ *     a thread-local message for the last failure on the calling thread;
+ *   - takes raw DEVICE pointers with explicit sizes / leading dimensions (in
+ *     elements) and a cudaStream_t passed as void*; work is enqueued on that
+ *     stream, nothing synchronises the host;
+ *   - never allocates or frees caller memory; scratch comes from a
+ *     caller-provided workspace sized by the matching *_workspace_bytes();
+ *   - matrices are row-major fp32; ids are int32 unless stated.
+ */
+#ifndef GTS_H_
+#define GTS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gts_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define GTS_API __attribute__((visibility("default")))
+#else
+#define GTS_API
+#endif
+
+enum gts_status {
+  GTS_OK = 0,
+  GTS_ERR_INVALID = 1,     /* bad argument (null pointer, negative size, misalignment) */
+  GTS_ERR_CUDA = 2,        /* a CUDA runtime/driver call failed */
+  GTS_ERR_WORKSPACE = 3,   /* workspace too small */
+  GTS_ERR_UNSUPPORTED = 4  /* shape/mode not supported by this build */
+};
+
+/* GEMM epilogues */
+enum gts_act {
+  GTS_ACT_NONE = 0,
+  GTS_ACT_RELU = 1,     /* C = max(acc + bias, 0) */
+  GTS_ACT_MASK_POS = 2  /* C = (aux > 0) ? acc + bias : 0   (ReLU backward mask) */
+};
+
+/* GEMM arithmetic */
+enum gts_gemm_mode {
+  GTS_GEMM_FP32 = 0,    /* SIMT FFMA, fp32 multiply + fp32 accumulate */
+  GTS_GEMM_TF32 = 1,    /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM */
+  GTS_GEMM_TF32X3 = 2   /* 3xTF32 split (hi*hi + hi*lo + lo*hi) on tcgen05: fp32-accurate */
+};
+
+GTS_API int gts_version(void);
+GTS_API const char* gts_last_error(void);
+/* SM count / compute capability of the current device (for grid sizing & gating). */
+GTS_API int gts_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ------------------------------------------------------------------------
+ * K6 — batched graph -> device CSR.
+ * Replaces dgl.batch + dgl.from_networkx + DGL's lazy COO->CSR
+ * (data_processing/data_loader.py:72,168; model/gnn_model.py:38).
+ * ------------------------------------------------------------------------ */
+
+/* Block-diagonal union: global ids = local ids + node_off[g(e)], where graph
+ * g(e) is the one whose edge range [edge_off[g], edge_off[g+1]) holds e.
+ * edge_off (int64, n_graphs+1) and node_off (int32, n_graphs+1) are device arrays. */
+GTS_API int gts_batch_edges(const int32_t* src_local, const int32_t* dst_local, int64_t n_edges,
+                    const int64_t* edge_off, const int32_t* node_off, int32_t n_graphs,
+                    int32_t* src_global, int32_t* dst_global, gts_stream_t stream);
+
+GTS_API size_t gts_csr_build_workspace_bytes(int64_t n_edges, int32_t n_nodes);
+
+/* Canonical CSR keyed by `row` (pass dst for the in-edge CSR, src for the
+ * out-edge CSC): indptr[n_nodes+1], indices[e] = col of the e-th entry, rows
+ * ordered by edge id (== stable sort of edge ids by row), eid[e] = original
+ * edge id (nullable).  Bit-exact with np.argsort(row, kind='stable'). */
+GTS_API int gts_csr_build(const int32_t* row, const int32_t* col, int64_t n_edges, int32_t n_nodes,
+                  int32_t* indptr, int32_t* indices, int32_t* eid,
+                  void* workspace, size_t workspace_bytes, gts_stream_t stream);
+
+/* csc2csr[q] = position in the CSR of the edge stored at CSC slot q.
+ * scratch: n_edges int32. */
+GTS_API int gts_edge_perm_compose(const int32_t* eid_csr, const int32_t* eid_csc, int64_t n_edges,
+                          int32_t* scratch, int32_t* csc2csr, gts_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * K1 / K3 / K4 — dense contractions.  Replace nn.Linear inside DGL SAGEConv /
+ * GATConv (invoked at model/networks.py:35,63,65) and their autograd.
+ * ------------------------------------------------------------------------ */
+
+/* C[M,N] = act( A1[M,K1] * B1[N,K1]^T + A2[M,K2] * B2[N,K2]^T + bias[N] ).
+ * B* use the nn.Linear weight layout [out,in].  A2/B2 may be NULL (K2 = 0):
+ * the two-source form is the concatenated fc_self || fc_neigh contraction
+ * without materialising the concatenation.  aux/ldaux: mask source for
+ * GTS_ACT_MASK_POS (same shape as C). */
+typedef struct gts_gemm_nt_args {
+  const float* A1; int64_t lda1; int32_t K1;
+  const float* A2; int64_t lda2; int32_t K2;
+  const float* B1; int64_t ldb1;
+  const float* B2; int64_t ldb2;
+  const float* bias;
+  const float* aux; int64_t ldaux;
+  float* C; int64_t ldc;
+  int32_t M; int32_t N;
+  int32_t act;   /* gts_act */
+  int32_t mode;  /* gts_gemm_mode */
+} gts_gemm_nt_args;
+
+GTS_API int gts_gemm_nt(const gts_gemm_nt_args* args, gts_stream_t stream);
+
+/* Weight gradient: C[Mo,No] = A[K,Mo]^T * B[K,No]  (K = number of nodes).
+ * Split-K over the grid with a deterministic second-pass reduction. */
+GTS_API size_t gts_gemm_tn_workspace_bytes(int32_t Mo, int32_t No, int64_t K, int32_t mode);
+GTS_API int gts_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb,
+                float* C, int64_t ldc, int32_t Mo, int32_t No, int64_t K, int32_t mode,
+                void* workspace, size_t workspace_bytes, gts_stream_t stream);
+
+/* out[c] = sum_r A[r,c]  (bias gradients).  Deterministic two-pass. */
+GTS_API size_t gts_colsum_workspace_bytes(int64_t rows, int32_t cols);
+GTS_API int gts_colsum(const float* A, int64_t lda, int64_t rows, int32_t cols, float* out,
+               void* workspace, size_t workspace_bytes, gts_stream_t stream);
+
+/* out[c, r] = in[r, c]  (small weight transposes for the data-gradient GEMMs). */
+GTS_API int gts_transpose(const float* in, int64_t ldin, int32_t rows, int32_t cols,
+                  float* out, int64_t ldout, gts_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * K2 / K2b — neighbour max-aggregation.  Replace DGL
+ * update_all(copy_src, max) and its scatter-add backward inside
+ * SAGEConv('pool') (invoked at model/networks.py:35).
+ * ------------------------------------------------------------------------ */
+
+/* neigh[v,k] = max_{u in row v} P[u,k]; argmax[v,k] = that u, FIRST maximum in
+ * CSR order wins; rows with no entries give 0 / -1.  argmax may be NULL
+ * (inference). */
+GTS_API int gts_segmax_fwd(const float* P, int64_t ldp, const int32_t* indptr, const int32_t* indices,
+                   int32_t n_nodes, int32_t D, float* neigh, int64_t ldn,
+                   int32_t* argmax, int64_t ldarg, gts_stream_t stream);
+
+/* dP[argmax[v,k], k] += dNeigh[v,k]; dP ([n_src_rows, D], leading dim lddp) is
+ * zero-filled by the call.  fp32 atomics (order not deterministic). */
+GTS_API int gts_segmax_bwd(const float* dNeigh, int64_t ldd, const int32_t* argmax, int64_t ldarg,
+                   int32_t n_nodes, int32_t D, float* dP, int64_t lddp, int32_t n_src_rows,
+                   gts_stream_t stream);
+
+/* Deterministic form: transposed gather over the out-edge CSC.
+ * dP[u,k] = sum over out-edges (u->v) with argmax[v,k]==u of dNeigh[v,k]. */
+GTS_API int gts_segmax_bwd_det(const float* dNeigh, int64_t ldd, const int32_t* argmax, int64_t ldarg,
+                       const int32_t* csc_indptr, const int32_t* csc_indices,
+                       int32_t n_nodes, int32_t D, float* dP, int64_t lddp, gts_stream_t stream);
+
+/* Sum-type aggregators of SAGEConv('mean'|'gcn') (model/networks.py:72-75):
+ * mode 0: sum; 1: mean over in-edges (0 if none); 2: gcn = (sum + self[v]) / (deg+1). */
+GTS_API int gts_segsum_fwd(const float* P, int64_t ldp, const int32_t* indptr, const int32_t* indices,
+                   int32_t n_nodes, int32_t D, int32_t mode, float* out, int64_t ldo,
+                   gts_stream_t stream);
+
+/* Backward of gts_segsum_fwd over the out-edge CSC:
+ * dP[u,k] = sum_{(u->v)} s(v) * dOut[v,k]  (+ s(u)*dOut[u,k] for gcn), with
+ * s(v) = 1 | 1/deg_in(v) | 1/(deg_in(v)+1) for mode 0 | 1 | 2; deg_in from in_indptr. */
+GTS_API int gts_segsum_bwd(const float* dOut, int64_t ldd, const int32_t* csc_indptr, const int32_t* csc_indices,
+                   const int32_t* in_indptr, int32_t n_nodes, int32_t D, int32_t mode,
+                   float* dP, int64_t lddp, gts_stream_t stream);
+
+/* out[i] = ref[i] > 0 ? grad[i] : 0   (stand-alone ReLU backward, used when the
+ * mask could not be fused into a GEMM epilogue). */
+GTS_API int gts_mask_pos(const float* grad, const float* ref, int64_t n, float* out, gts_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * K8 — weighted-mean cross entropy (model/gnn_model.py:30,42).
+ * ------------------------------------------------------------------------ */
+
+/* sums[0] += sum_i w[y_i]*nll_i ; sums[1] += sum_i w[y_i]  (caller zeroes sums);
+ * dlogits[i,c] = w[y_i]*(softmax(z_i)[c] - [c==y_i])   (NOT yet divided by
+ * sums[1]; nullable).  labels are int64 as torch.LongTensor. */
+GTS_API int gts_ce_weighted(const float* logits, int64_t ld, const int64_t* labels, const float* class_w,
+                    int32_t n_nodes, int32_t n_classes, float* sums, float* dlogits, int64_t ldd,
+                    gts_stream_t stream);
+
+/* x[i] *= alpha / (*denom)   (denominator read on the device: no host sync). */
+GTS_API int gts_scale_by_inv(float* x, int64_t n, float alpha, const float* denom, gts_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * K7 — node -> voxel reprojection.
+ * ------------------------------------------------------------------------ */
+
+/* cls[i] = index of the first maximum of logits[i,:]  (torch.max(logits,1),
+ * scripts/generate_gnn_predictions.py:66; model/gnn_model.py:65). */
+GTS_API int gts_argmax_rows(const float* logits, int64_t ld, int32_t n_nodes, int32_t n_classes,
+                    int32_t* cls, gts_stream_t stream);
+
+/* project_nodes_to_img (data_processing/graph_io.py:21-24):
+ * out[i] = svs[i] == -1 ? 0 : node_labels[svs[i]].  err_flag (device int32,
+ * caller zeroes) is set to 1 if an id is outside [-1, n_nodes). */
+GTS_API int gts_project_nodes(const int16_t* svs, int64_t n_vox, const int64_t* node_labels,
+                      int32_t n_nodes, int64_t* out, int32_t* err_flag, gts_stream_t stream);
+
+/* save_voxel_preds minus the NIfTI write
+ * (scripts/generate_gnn_predictions.py:64-73): project int32 node classes
+ * through the cropped int16 map, paste into the full volume
+ * (uncrop_to_brats_size, data_processing/image_processing.py:21-25) and
+ * relabel through lut (swap_labels_to_brats, scripts/preprocess_dataset.py:159-169).
+ * inv_x/inv_y/inv_z (lengths VX,VY,VZ): crop coordinate of each full-volume
+ * plane or -1.  Every voxel of vol[VX,VY,VZ] is written exactly once.
+ * err_flag set to 1 on an id outside [-1,n_nodes) or a class outside [0,n_lut). */
+GTS_API int gts_project_labels(const int16_t* svs, int32_t X, int32_t Y, int32_t Z,
+                       const int32_t* inv_x, const int32_t* inv_y, const int32_t* inv_z,
+                       const int32_t* node_cls, int32_t n_nodes,
+                       const int16_t* lut, int32_t n_lut,
+                       int16_t* vol, int32_t VX, int32_t VY, int32_t VZ,
+                       int32_t* err_flag, gts_stream_t stream);
+
+/* save_voxel_logits (scripts/generate_gnn_predictions.py:55-62;
+ * scripts/generate_joint_predictions.py:64-66): out[i,:] = svs[i]==-1 ?
+ * bg_row : node_logits[svs[i],:]. */
+GTS_API int gts_project_logits(const int16_t* svs, int64_t n_vox, const float* node_logits, int64_t ld,
+                       int32_t n_nodes, int32_t n_classes, const float* bg_row, float* out,
+                       int32_t* err_flag, gts_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * K5 — GATConv edge-score + edge-softmax + weighted aggregation, fused
+ * (DGL GATConv.forward invoked at model/networks.py:63,65).
+ * Z is [n_nodes, H*F] (ldz), el/er/rowmax/rowsum are [n_nodes, H].
+ * ------------------------------------------------------------------------ */
+
+/* el[u,h] = <Z[u,h,:], attn_l[h,:]>, er likewise. */
+GTS_API int gts_gat_scores(const float* Z, int64_t ldz, const float* attn_l, const float* attn_r,
+                   int32_t n_nodes, int32_t H, int32_t F, float* el, float* er, gts_stream_t stream);
+
+/* out[v,h,:] = act( sum_{e=(u->v)} softmax_e(leaky_relu(el[u,h]+er[v,h])) * Z[u,h,:]
+ *                   + res[v,h,:] + bias[h,:] ),  act: 0 none, 1 ELU.
+ * rowmax/rowsum save the softmax statistics for the backward.  A row with no
+ * in-edges sets *err_flag = 1 (DGL raises DGLError). */
+GTS_API int gts_gat_fwd(const float* Z, int64_t ldz, const float* el, const float* er,
+                const int32_t* indptr, const int32_t* indices,
+                int32_t n_nodes, int32_t H, int32_t F, float slope,
+                const float* res, int64_t ldres, const float* bias, int32_t act,
+                float* out, int64_t ldo, float* rowmax, float* rowsum,
+                int32_t* err_flag, gts_stream_t stream);
+
+/* dpre = dout * ELU'(out) (act==1) or dout (act==0). */
+GTS_API int gts_gat_act_bwd(const float* dout, const float* out, int64_t n, int32_t act, float* dpre,
+                    gts_stream_t stream);
+
+/* Backward pass A (by destination): per edge dt[e,h] (CSR order), der[v,h]. */
+GTS_API int gts_gat_bwd_dst(const float* Z, int64_t ldz, const float* el, const float* er,
+                    const float* rowmax, const float* rowsum,
+                    const int32_t* indptr, const int32_t* indices,
+                    const float* dO, int64_t lddo,
+                    int32_t n_nodes, int32_t H, int32_t F, float slope,
+                    float* dt_edge, float* der, gts_stream_t stream);
+
+/* Backward pass B (by source, over the out-edge CSC): dZ[u,h,:] =
+ * sum_{e=(u->v)} alpha_e*dO[v,h,:] + del[u,h]*attn_l[h,:] + der[u,h]*attn_r[h,:];
+ * del[u,h] = sum_{out(u)} dt_e is also written. */
+GTS_API int gts_gat_bwd_src(const float* el, const float* er, const float* rowmax, const float* rowsum,
+                    const int32_t* csc_indptr, const int32_t* csc_indices, const int32_t* csc2csr,
+                    const float* dO, int64_t lddo, const float* dt_edge, const float* der,
+                    const float* attn_l, const float* attn_r,
+                    int32_t n_nodes, int32_t H, int32_t F, float slope,
+                    float* dZ, int64_t lddz, float* del, gts_stream_t stream);
+
+/* dattn[h,f] = sum_u coef[u,h] * Z[u,h,f]   (gradients of attn_l / attn_r). */
+GTS_API size_t gts_gat_attn_grad_workspace_bytes(int32_t n_nodes, int32_t H, int32_t F);
+GTS_API int gts_gat_attn_grad(const float* Z, int64_t ldz, const float* coef, int32_t n_nodes,
+                      int32_t H, int32_t F, float* dattn, void* workspace, size_t workspace_bytes,
+                      gts_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Optimiser step on a flat parameter arena (model/gnn_model.py:28,46):
+ * AdamW exactly as torch.optim.AdamW (decoupled weight decay, bias
+ * correction), grads pre-scaled by grad_scale / (*grad_denom) when
+ * grad_denom != NULL (data-parallel loss denominator).
+ * ------------------------------------------------------------------------ */
+GTS_API int gts_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                   float grad_scale, const float* grad_denom, gts_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GTS_H_ */

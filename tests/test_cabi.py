@@ -1,0 +1,57 @@
+"""The C-ABI library loads and exports every symbol include/gts.h declares
+(no compute calls: runs without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "gts.h")).read()
+    return sorted(set(re.findall(r"GTS_API\s+[\w\s\*]+?\b(gts_\w+)\s*\(", txt)))
+
+
+def test_header_declares_expected_families():
+    syms = _declared_symbols()
+    assert len(syms) >= 30
+    for s in ("gts_csr_build", "gts_gemm_nt", "gts_gemm_tn", "gts_segmax_fwd", "gts_segmax_bwd", "gts_gat_fwd",
+              "gts_project_labels", "gts_ce_weighted", "gts_last_error"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    for s in _declared_symbols():
+        assert hasattr(built_lib, s), f"{s} declared in gts.h but not exported by libgts.so"
+
+
+def test_binding_table_matches_header(built_lib):
+    from gnn_tumor_seg_b200 import _lib
+    assert sorted(_lib.EXPORTED_SYMBOLS) == _declared_symbols()
+
+
+def test_version_and_error_string(built_lib):
+    assert built_lib.gts_version() >= 100
+    assert isinstance(built_lib.gts_last_error(), bytes)
+
+
+def test_argument_validation_without_gpu(built_lib):
+    """Argument checks run before any CUDA call, so they are testable on CPU."""
+    from gnn_tumor_seg_b200 import _lib
+    rc = built_lib.gts_csr_build(None, None, -1, 4, None, None, None, None, 0, None)
+    assert rc == 1 and b"negative" in built_lib.gts_last_error()
+    rc = built_lib.gts_gemm_nt(None, None)
+    assert rc == 1
+    assert built_lib.gts_csr_build_workspace_bytes(1000, 100) > 0
+    assert built_lib.gts_gemm_tn_workspace_bytes(256, 512, 90000, 0) >= 256 * 512 * 4
+    with pytest.raises(_lib.GtsError):
+        _lib.check(rc, "gts_gemm_nt")
+
+
+def test_gemm_args_struct_layout():
+    from gnn_tumor_seg_b200._lib import GemmNtArgs
+    # matches the C struct under the SysV x86-64 ABI (natural alignment)
+    assert ctypes.sizeof(GemmNtArgs) == 136
+    assert GemmNtArgs.K1.offset == 16 and GemmNtArgs.A2.offset == 24 and GemmNtArgs.mode.offset == 132
