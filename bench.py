@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (BASELINE.json):
+GraphSAGE-pool 7x256 training step (forward + weighted CE + backward
+[+ gradient all-reduce]) on batches of 6 synthetic 15k-node supervoxel RAGs.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # reference-equivalent CPU path (oracle)
+
+Prints ONE JSON line on rank 0 (contract in the task statement): `value` =
+whole-job graphs/s with inputs resident in HBM; `e2e` = the same metric through
+the public API from pinned HOST buffers (H2D of edge lists/features/labels, the
+device CSR build, forward, loss, backward, D2H read of the loss) — all inside
+the timed region; `roofline` for the dominant kernel; `cpu_baseline` = the CPU
+oracle timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("GTS_SYNTH_CACHE", os.path.join(ROOT, ".synth_cache"))
+
+import numpy as np
+import torch
+
+LAYER_SIZES = [256] * 7
+IN_FEATS, N_CLASSES = 20, 4
+CLASS_W = [0.1, 1.0, 2.0, 2.0]
+N_DISTINCT_GRAPHS = 8
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synth_batches(batch, n_batches, rank):
+    from gnn_tumor_seg_b200 import synth
+    graphs = [synth.make_graph(s) for s in range(N_DISTINCT_GRAPHS)]
+    out = []
+    for b in range(n_batches):
+        ids = [(rank * 3 + b * batch + i) % N_DISTINCT_GRAPHS for i in range(batch)]
+        out.append([graphs[i] for i in ids])
+    return out
+
+
+def model_flops_bytes(n_nodes, n_edges):
+    """Algorithmic fwd+bwd flops of the 7x256 stack: fwd = sum over layers of
+    2*N*Din^2 (fc_pool) + 2*N*2Din*Dout (concat GEMM); fwd+bwd ~ 3x."""
+    dims = [IN_FEATS] + LAYER_SIZES + [N_CLASSES]
+    fwd = 0
+    for din, dout in zip(dims[:-1], dims[1:]):
+        fwd += 2 * n_nodes * din * din + 2 * n_nodes * 2 * din * dout
+    return 3 * fwd
+
+
+# ---------------------------------------------------------------------------
+# reference arm: the reference-equivalent CPU path (DGL cannot be installed offline)
+# ---------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import graph_ref, sage_ref
+    from gnn_tumor_seg_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = synth.make_graph(0)
+    indptr, indices, _ = graph_ref.csr_by_dst_ref(g.src, g.dst, g.n_nodes)
+    torch.manual_seed(0)
+    net = sage_ref.GraphSageRef(IN_FEATS, LAYER_SIZES, N_CLASSES)
+    x, y, w = torch.as_tensor(g.features), torch.as_tensor(g.labels), torch.tensor(CLASS_W)
+
+    def step():
+        net.zero_grad()
+        loss = torch.nn.functional.cross_entropy(net((indptr, indices), x), y, weight=w)
+        loss.backward()
+        return float(loss)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    gps = 1.0 / dt
+    sample = "1 of the 6 graphs of a batch per step (15000 nodes, %d edges), fwd+CE+bwd" % g.n_edges
+    line = {
+        "impl": "reference", "metric": "graphs_per_s", "value": gps, "unit": "graphs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "edges_per_s": gps * g.n_edges,
+        "config": {"workload": "GraphSAGE-pool 7x256 training fwd+bwd, synthetic 15k-node supervoxel RAGs (BASELINE configs[1])",
+                   "note": "reference-equivalent CPU path: pure-PyTorch restatement of DGL SAGEConv('pool'); DGL is not installable offline",
+                   "threads": torch.get_num_threads()},
+        "cpu_baseline": {"value": gps, "unit": "graphs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": gps, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+def time_kernel(fn, n_iter, stream_sync=True):
+    """Average device time of fn(i) over n_iter calls (CUDA events on the current stream)."""
+    for i in range(3):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n_iter):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n_iter     # ms
+
+
+def kernel_breakdown(step_fn, ops):
+    """One instrumented step: CUDA-event time of every libgts call class."""
+    names = ["gemm_nt", "gemm_tn", "segmax_fwd", "segmax_bwd", "colsum", "transpose", "mask_pos", "ce_weighted",
+             "scale_by_inv_"]
+    orig = {n: getattr(ops, n) for n in names}
+    records = []
+
+    def wrap(n):
+        f = orig[n]
+
+        def g(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = f(*a, **k)
+            e1.record()
+            records.append((n, e0, e1))
+            return r
+        return g
+
+    try:
+        for n in names:
+            setattr(ops, n, wrap(n))
+        step_fn()
+        torch.cuda.synchronize()
+    finally:
+        for n in names:
+            setattr(ops, n, orig[n])
+    out = {}
+    for n, e0, e1 in records:
+        d = out.setdefault(n, {"ms": 0.0, "calls": 0})
+        d["ms"] += e0.elapsed_time(e1)
+        d["calls"] += 1
+    return out
+
+
+def run_ours(args):
+    from gnn_tumor_seg_b200 import dp, graph as G, networks, ops, _lib
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU baseline")
+    _lib.load()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    ops.set_gemm_mode(args.mode)
+    peaks = load_peaks()
+
+    # ---- synthetic inputs (rank 0 fills the cache first) ----
+    if world > 1:
+        if rank == 0:
+            synth_batches(args.batch, 1, 0)
+        torch.distributed.barrier()
+    host_batches = synth_batches(args.batch, args.rotate, rank)
+    pinned = []
+    for graphs in host_batches:
+        bg = G.batch([G.from_edge_list(g.src, g.dst, g.n_nodes) for g in graphs], pin=True)
+        feats = torch.as_tensor(np.concatenate([g.features for g in graphs])).pin_memory()
+        labels = torch.as_tensor(np.concatenate([g.labels for g in graphs])).pin_memory()
+        pinned.append((bg, feats, labels))
+    resident = [(bg.to(dev), f.to(dev), l.to(dev)) for bg, f, l in pinned]
+    n_nodes = resident[0][0].number_of_nodes()
+    n_edges = resident[0][0].number_of_edges()
+
+    torch.manual_seed(0)
+    net = networks.GraphSage(IN_FEATS, LAYER_SIZES, N_CLASSES, "pool", 0).to(dev)
+    class_w = torch.tensor(CLASS_W, device=dev)
+    trainer = dp.DataParallelTrainer(net, class_w)
+
+    def step(i):
+        bg, f, l = resident[i % len(resident)]
+        return trainer.forward_backward(bg, f, l)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = ops.launch_counter["n"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step(i)
+    e1.record()
+    barrier()
+    launches = ops.launch_counter["n"] - n0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1) / args.steps
+    loss_val = float(loss)
+
+    # ---- end to end from pinned host buffers through the public API ----
+    def e2e_step(i):
+        bg, f, l = pinned[i % len(pinned)]
+        dg = bg.to(dev)                                    # H2D edge lists + device CSR build
+        ls = trainer.forward_backward(dg, f.to(dev, non_blocking=True), l.to(dev, non_blocking=True))
+        return float(ls)                                   # D2H read of the step's loss
+
+    for i in range(max(3, args.warmup // 2)):
+        e2e_step(i)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1) / args.steps
+    h2d = n_edges * 8 + (args.batch + 1) * 12 + n_nodes * IN_FEATS * 4 + n_nodes * 8
+    d2h = 4
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.barrier()
+            torch.distributed.destroy_process_group()
+        return
+
+    # ---- per-kernel breakdown and live roofline of the dominant + aggregation kernels ----
+    breakdown = kernel_breakdown(lambda: step(0), ops)
+    D = 256
+    Ps = [torch.relu(torch.randn(n_nodes, D, device=dev)) for _ in range(3)]      # 3 x 92 MB > L2
+    indptr, indices = resident[0][0].csr
+    ms_seg = time_kernel(lambda i: ops.segmax_fwd(Ps[i % 3], indptr, indices, want_argmax=True), 30)
+    seg_bytes = 4 * (3 * n_nodes * D + (n_nodes + 1) + n_edges)
+    seg_gbs = seg_bytes / (ms_seg * 1e-3) / 1e9
+    args_ = [ops.segmax_fwd(Ps[i], indptr, indices)[1] for i in range(3)]
+    dNs = [torch.randn(n_nodes, D, device=dev) for _ in range(3)]
+    ms_segb = time_kernel(lambda i: ops.segmax_bwd(dNs[i % 3], args_[i % 3], n_nodes), 30)
+    segb_bytes = 4 * (4 * n_nodes * D)            # dNeigh + argmax reads, dP zero-fill + dP atomics
+    W = torch.randn(D, D, device=dev)
+    bias = torch.randn(D, device=dev)
+    ms_gemm = time_kernel(lambda i: ops.gemm_nt(Ps[i % 3], W, Ps[(i + 1) % 3], W, bias=bias, act=1), 10)
+    gemm_flops = 2.0 * n_nodes * 2 * D * D
+    gemm_tflops = gemm_flops / (ms_gemm * 1e-3) / 1e12
+    tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+    passes = {"fp32": 1, "tf32": 1, "tf32x3": 3}[args.mode]
+    kern = {
+        "segmax_fwd": {"ms": ms_seg, "bound": "hbm", "achieved": seg_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                       "frac": seg_gbs / peaks["hbm_gbs"], "alg_bytes": seg_bytes},
+        "segmax_bwd": {"ms": ms_segb, "bound": "hbm", "achieved": segb_bytes / (ms_segb * 1e-3) / 1e9,
+                       "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                       "frac": segb_bytes / (ms_segb * 1e-3) / 1e9 / peaks["hbm_gbs"], "alg_bytes": segb_bytes},
+        "gemm_concat_k512": {"ms": ms_gemm, "bound": "tensor", "achieved": gemm_tflops, "peak": tf32_peak,
+                             "unit": "TFLOP/s", "frac": gemm_tflops / tf32_peak, "alg_flops": gemm_flops,
+                             "mma_passes": passes,
+                             "peak_note": "TF32 dense peak taken as 1/2 of the measured sustained bf16 cuBLAS figure"},
+    }
+    tot = sum(v["ms"] for v in breakdown.values()) or 1.0
+    share = {k: {"ms": round(v["ms"], 4), "calls": v["calls"], "share": round(v["ms"] / tot, 4)}
+             for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])}
+    dominant = next(iter(share))
+    if dominant in ("gemm_nt", "gemm_tn"):
+        gemm_ms = breakdown["gemm_nt"]["ms"] + breakdown.get("gemm_tn", {"ms": 0})["ms"]
+        flops = model_flops_bytes(n_nodes, n_edges)
+        ach = flops / (gemm_ms * 1e-3) / 1e12
+        roofline = {"kernel": "gemm (tcgen05 tf32)" if args.mode != "fp32" else "gemm (simt fp32)", "bound": "tensor",
+                    "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None,
+                    "note": "algorithmic fwd+bwd flops of the step / summed GEMM launch time in the step; "
+                            "peak = 1/2 measured sustained bf16 (%s)" % peaks["src"]}
+    else:
+        k = kern["segmax_fwd"]
+        roofline = {"kernel": "segmax_fwd", "bound": "hbm", "achieved": k["achieved"], "peak": k["peak"],
+                    "unit": "GB/s", "frac": k["frac"], "traffic": None,
+                    "note": "algorithmic bytes 4*(3*N*D + N+1 + E) / CUDA-event time; peak %s" % peaks["src"]}
+
+    # ---- CPU baseline (oracle, bounded sample) ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import graph_ref, sage_ref
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        g = host_batches[0][0]
+        ip, ix, _ = graph_ref.csr_by_dst_ref(g.src, g.dst, g.n_nodes)
+        torch.manual_seed(0)
+        ref = sage_ref.GraphSageRef(IN_FEATS, LAYER_SIZES, N_CLASSES)
+        x, y, w = torch.as_tensor(g.features), torch.as_tensor(g.labels), torch.tensor(CLASS_W)
+
+        def cstep():
+            ref.zero_grad()
+            torch.nn.functional.cross_entropy(ref((ip, ix), x), y, weight=w).backward()
+        cstep()
+        t0 = time.perf_counter()
+        n_c = 0
+        while n_c < 3 or (time.perf_counter() - t0 < 12 and n_c < 10):
+            cstep()
+            n_c += 1
+        dt = (time.perf_counter() - t0) / n_c
+        cpu = {"value": 1.0 / dt, "unit": "graphs/s", "cores": cores, "kind": "port",
+               "sample": "%d x (1 graph of the batch: 15000 nodes, %d edges) fwd+CE+bwd, PyTorch CPU oracle "
+                         "(DGL not installable offline)" % (n_c, g.n_edges)}
+
+    total_graphs = args.batch * world
+    line = {
+        "metric": "graphs_per_s", "value": total_graphs / (ms * 1e-3), "unit": "graphs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3"}[args.mode], "data": "synthetic",
+        "edges_per_s": n_edges * world / (ms * 1e-3),
+        "config": {"workload": "GraphSAGE-pool 7x256 training fwd+CE+bwd, batch of 6 synthetic 15k-node supervoxel RAGs per GPU "
+                               "(BASELINE configs[1]; configs[3] for N>1: whole graphs per rank + one NCCL grad all-reduce)",
+                   "layer_sizes": LAYER_SIZES, "graphs_per_gpu": args.batch, "nodes_per_step_per_gpu": n_nodes,
+                   "edges_per_step_per_gpu": n_edges, "gemm_mode": args.mode,
+                   "l2_policy": "inputs larger than L2: %d rotating device-resident batches, >2 GB of activations per step" % args.rotate,
+                   "parallelism": "dp%d" % world},
+        "clocks": clocks,
+        "e2e": {"value": total_graphs / (ms_e2e * 1e-3), "unit": "graphs/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "kernels": kern,
+        "step_breakdown": share,
+        "loss": loss_val,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("GTS_GEMM_MODE", "tf32x3"), choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--batch", type=int, default=6)
+    ap.add_argument("--rotate", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -7,7 +7,8 @@ preprocessing produces for ``-k 0`` (true region adjacency):
 * partition: int16 supervoxel map over the BraTS volume (240,240,155), -1 =
   background, ids 0..N-1 (reference: mri2graph/graphgen.py:71-90,243 — SLIC
   followed by discard_empty_svs; here a Voronoi partition of an ellipsoidal
-  "brain", SLIC needs skimage which is absent);
+  "brain", SLIC needs skimage which is absent); ids are numbered in raster
+  order of a coarse grid like SLIC's grid-initialised clusters;
 * graph: 6-connectivity region adjacency with a self-loop on every node, as
   mri2graph/graphgen.py:161-196 (find_adjacent_nodes) builds it, returned as
   the directed edge list dgl.from_networkx would see (lexicographic (src,dst),
@@ -93,6 +94,14 @@ def voronoi_partition(seed: int, n_seeds: int = 15000, shape=BRATS_SHAPE,
         cand = cand[(cand ** 2).sum(1) <= 1.0]
         seeds = np.concatenate([seeds, cand * r + c])
     seeds = seeds[:n_seeds]
+    # SLIC (mri2graph/graphgen.py:243) initialises its clusters on a regular grid and numbers
+    # them in C (raster) order, so real supervoxel ids are spatially coherent: consecutive ids
+    # are neighbours in space.  Give the synthetic ids the same property: order the seeds by
+    # the raster index of a coarse grid cell (x, then y, then z fastest).  This only relabels
+    # nodes — edge count and degree statistics are unchanged.
+    cell = 6.0
+    key = (np.floor(seeds[:, 0] / cell) * 4096 + np.floor(seeds[:, 1] / cell)) * 4096 + np.floor(seeds[:, 2] / cell)
+    seeds = seeds[np.argsort(key, kind="stable")]
     _, owner = cKDTree(seeds).query(pts, workers=-1)
     uniq, compact = np.unique(owner, return_inverse=True)
     vol = np.full(shape, -1, dtype=np.int16)
@@ -122,10 +131,10 @@ def make_graph(g: int, n_seeds: int = 15000, with_partition: bool = False,
     """Synthetic graph ``g`` (partition seed = g, node-data seed = 1000+g)."""
     cache = None
     if cache_dir is None:
-        cache_dir = os.environ.get("GTS_SYNTH_CACHE", "/tmp/gts_synth_cache")
+        cache_dir = os.environ.get("GTS_SYNTH_CACHE") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), ".synth_cache")
     if cache_dir:
         os.makedirs(cache_dir, exist_ok=True)
-        cache = os.path.join(cache_dir, f"rag_s{g}_n{n_seeds}.npz")
+        cache = os.path.join(cache_dir, f"rag_raster_s{g}_n{n_seeds}.npz")
     if cache and os.path.exists(cache):
         z = np.load(cache)
         n_nodes, src, dst = int(z["n_nodes"]), z["src"], z["dst"]

@@ -1,0 +1,99 @@
+"""GPU parity: dense contractions (all arithmetic modes), column sums,
+transposes, weighted CE — against fp64 PyTorch on the CPU.
+Tolerances (relative to the largest reference magnitude): fp32 1e-5,
+tf32x3 2e-5 (fp32-accurate 3xTF32), tf32 2e-3 (10-bit mantissa inputs)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gnn_tumor_seg_b200 import ops
+from gnn_tumor_seg_b200._lib import ACT_MASK_POS, ACT_NONE, ACT_RELU
+
+pytestmark = pytest.mark.gpu
+TOL = {"fp32": 1e-5, "tf32x3": 2e-5, "tf32": 2e-3}
+
+
+def _rel(a, b):
+    return (a.double() - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3", "tf32"])
+@pytest.mark.parametrize("M,N,K1,K2", [(1000, 256, 256, 256), (333, 256, 20, 20), (700, 4, 256, 256),
+                                       (129, 256, 256, 0), (4097, 128, 64, 32), (5, 16, 8, 0), (2048, 256, 4, 256)])
+def test_gemm_nt(cuda_dev, mode, M, N, K1, K2):
+    g = torch.Generator().manual_seed(M + N + K1)
+    A1 = torch.randn(M, K1, generator=g); B1 = torch.randn(N, K1, generator=g)
+    A2 = torch.randn(M, K2, generator=g) if K2 else None
+    B2 = torch.randn(N, K2, generator=g) if K2 else None
+    bias = torch.randn(N, generator=g); aux = torch.randn(M, N, generator=g)
+    ref = A1.double() @ B1.double().T + bias.double()
+    if K2:
+        ref = ref + A2.double() @ B2.double().T
+    dv = lambda t: None if t is None else t.to(cuda_dev)
+    out = ops.gemm_nt(dv(A1), dv(B1), dv(A2), dv(B2), bias=dv(bias), act=ACT_NONE, mode=mode)
+    assert _rel(out.cpu(), ref) < TOL[mode]
+    out = ops.gemm_nt(dv(A1), dv(B1), dv(A2), dv(B2), bias=dv(bias), act=ACT_RELU, mode=mode)
+    assert _rel(out.cpu(), torch.relu(ref)) < TOL[mode]
+    out = ops.gemm_nt(dv(A1), dv(B1), dv(A2), dv(B2), bias=None, act=ACT_MASK_POS, aux=dv(aux), mode=mode)
+    assert _rel(out.cpu(), (ref - bias.double()) * (aux > 0)) < TOL[mode]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3", "tf32"])
+@pytest.mark.parametrize("K,Mo,No", [(5000, 256, 256), (90000, 256, 256), (1234, 4, 256), (777, 256, 20), (300, 20, 20),
+                                     (40000, 128, 64)])
+def test_gemm_tn(cuda_dev, mode, K, Mo, No):
+    g = torch.Generator().manual_seed(K + Mo)
+    A = torch.randn(K, Mo, generator=g); B = torch.randn(K, No, generator=g)
+    ref = A.double().T @ B.double()
+    out = ops.gemm_tn(A.to(cuda_dev), B.to(cuda_dev), mode=mode)
+    assert _rel(out.cpu(), ref) < TOL[mode]
+
+
+def test_gemm_strided_operands(cuda_dev):
+    big = torch.randn(300, 512)
+    A = big[:, 128:384]                       # ld 512
+    W = torch.randn(256, 256)
+    ref = A.double() @ W.double().T
+    for mode in ("fp32", "tf32x3"):
+        out = ops.gemm_nt(big.to(cuda_dev)[:, 128:384], W.to(cuda_dev), mode=mode)
+        assert _rel(out.cpu(), ref) < TOL[mode]
+
+
+def test_colsum_transpose_maskpos(cuda_dev):
+    for rows, cols in [(90000, 256), (1000, 4), (1, 20), (4097, 33)]:
+        A = torch.randn(rows, cols)
+        assert _rel(ops.colsum(A.to(cuda_dev)).cpu(), A.double().sum(0)) < 1e-5
+    W = torch.randn(37, 256)
+    assert torch.equal(ops.transpose(W.to(cuda_dev)).cpu(), W.T.contiguous())
+    g, r = torch.randn(1000, 7), torch.randn(1000, 7)
+    assert torch.equal(ops.mask_pos(g.to(cuda_dev), r.to(cuda_dev)).cpu(), g * (r > 0))
+
+
+def test_weighted_ce_forward_backward(cuda_dev):
+    torch.manual_seed(0)
+    z = (3 * torch.randn(5000, 4)).requires_grad_(True)
+    y = torch.randint(0, 4, (5000,)); w = torch.tensor([0.1, 1., 2., 2.])
+    ref = F.cross_entropy(z.double(), y, weight=w.double())
+    ref.backward()
+    zd = z.detach().to(cuda_dev).requires_grad_(True)
+    loss = ops.weighted_cross_entropy(zd, y.to(cuda_dev), w.to(cuda_dev))
+    loss.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
+    assert _rel(zd.grad.cpu(), z.grad.double()) < 1e-5
+
+
+def test_adamw_step_matches_torch(cuda_dev):
+    from gnn_tumor_seg_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(1)
+    p0 = torch.randn(10000); grads = [torch.randn(10000) for _ in range(3)]
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([p_ref], lr=1e-2, weight_decay=1e-2)
+    p = p0.clone().to(cuda_dev); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    for t, g in enumerate(grads, 1):
+        p_ref.grad = g.clone(); opt.step()
+        gd = g.to(cuda_dev)
+        _lib.check(lib.gts_adamw_step(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
+                                      1e-2, 0.9, 0.999, 1e-8, 1e-2, t, 1.0, None, _lib.stream_ptr()))
+    assert torch.allclose(p.cpu(), p_ref.detach(), atol=1e-6, rtol=1e-5)

@@ -1,0 +1,232 @@
+"""GPU parity end to end: SAGEConv('pool') layer and GraphSage stack, the
+mean/gcn aggregators, GATConv layer and GAT stack — logits and every parameter
+gradient vs the CPU oracle.  Tolerance: 1e-4 relative (fp32 / 3xTF32, fp32
+accumulate), 1e-3-class for plain TF32 — north_star's bar, stated per mode."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gnn_tumor_seg_b200 import graph as G, networks, ops, synth
+from oracle import gat_ref, graph_ref, sage_ref
+
+pytestmark = pytest.mark.gpu
+MODE_TOL = {"fp32": 1e-4, "tf32x3": 1e-4, "tf32": 5e-3}
+
+
+def _rel(a, b):
+    """max |a-b| / max |b|  (logits, activations)."""
+    return (a.double() - b.double()).abs().max().item() / max(b.double().abs().max().item(), 1e-30)
+
+
+def _rel_norm(a, b):
+    """||a-b||_F / ||b||_F  (gradients).  The network is piecewise linear: an arg-max or ReLU
+    decision that flips under fp32 rounding moves one whole gradient contribution, so a
+    max-norm over ~1e6 such decisions is not a stable metric; the norm-wise error is."""
+    return (a.double() - b.double()).norm().item() / max(b.double().norm().item(), 1e-30)
+
+
+def _batch(seeds, n_nodes=400, isolated=0, **kw):
+    gs = [synth.make_small_graph(s, n_nodes=n_nodes + 17 * i, isolated=isolated, **kw) for i, s in enumerate(seeds)]
+    bg = G.batch([G.from_edge_list(g.src, g.dst, g.n_nodes) for g in gs])
+    feats = torch.as_tensor(np.concatenate([g.features for g in gs]))
+    labels = torch.as_tensor(np.concatenate([g.labels for g in gs]))
+    s, d = bg.edges()
+    csr = graph_ref.csr_by_dst_ref(s.numpy(), d.numpy(), bg.number_of_nodes())[:2]
+    return bg, feats, labels, csr, (s, d)
+
+
+def _compare_grads(net, ref, tol):
+    for (n, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None, n
+        assert _rel_norm(p.grad.cpu(), q.grad) < tol, f"grad {n}: {_rel_norm(p.grad.cpu(), q.grad)}"
+        assert _rel(p.grad.cpu(), q.grad) < 50 * tol, f"grad {n} (max-norm): {_rel(p.grad.cpu(), q.grad)}"
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3", "tf32"])
+@pytest.mark.parametrize("deterministic", [False, True])
+def test_graphsage_pool_stack_fwd_bwd(cuda_dev, mode, deterministic):
+    ops.set_gemm_mode(mode)
+    ops.set_deterministic_backward(deterministic)
+    try:
+        bg, feats, labels, csr, _ = _batch([1, 2, 3], isolated=3)
+        torch.manual_seed(0)
+        net = networks.GraphSage(20, [256, 256, 64], 4, "pool", 0)
+        ref = sage_ref.GraphSageRef(20, [256, 256, 64], 4)
+        ref.load_state_dict(net.state_dict())
+        net.to(cuda_dev)
+        w = torch.tensor([0.1, 1., 2., 2.])
+        x = feats.to(cuda_dev).requires_grad_(True)
+        logits = net(bg.to(cuda_dev), x)
+        loss = ops.weighted_cross_entropy(logits, labels.to(cuda_dev), w.to(cuda_dev))
+        loss.backward()
+        xr = feats.clone().requires_grad_(True)
+        rl = ref(csr, xr)
+        rloss = F.cross_entropy(rl, labels, weight=w)
+        rloss.backward()
+        tol = MODE_TOL[mode]
+        assert _rel(logits.detach().cpu(), rl.detach()) < tol
+        assert abs(loss.item() - rloss.item()) < tol * max(1.0, abs(rloss.item()))
+        _compare_grads(net, ref, tol)
+        assert _rel_norm(x.grad.cpu(), xr.grad) < tol
+    finally:
+        ops.set_gemm_mode("tf32x3")
+        ops.set_deterministic_backward(False)
+
+
+def test_sage_layer_standalone_and_argmax_parity(cuda_dev):
+    """A single layer called like DGL's SAGEConv(graph, feat) — no stack flags —
+    and the arg-max of its pooled features bit-exact in fp32 mode."""
+    ops.set_gemm_mode("fp32")
+    try:
+        bg, feats, _, csr, _ = _batch([5], n_nodes=500)
+        torch.manual_seed(1)
+        layer = networks.SAGEConv(20, 32, "pool", activation=F.relu)
+        ref = sage_ref.SAGEConvPoolRef(20, 32, F.relu)
+        ref.load_state_dict(layer.state_dict())
+        layer.to(cuda_dev)
+        x = feats.to(cuda_dev).requires_grad_(True)
+        out = layer(bg.to(cuda_dev), x)
+        out.square().sum().backward()
+        xr = feats.clone().requires_grad_(True)
+        ro = ref(csr, xr)
+        ro.square().sum().backward()
+        assert _rel(out.detach().cpu(), ro.detach()) < 1e-5
+        assert _rel_norm(x.grad.cpu(), xr.grad) < 1e-4
+        _compare_grads(layer, ref, 1e-4)
+    finally:
+        ops.set_gemm_mode("tf32x3")
+
+
+def test_inference_no_grad_and_eval_argmax_agreement(cuda_dev):
+    bg, feats, _, csr, _ = _batch([7, 8])
+    torch.manual_seed(2)
+    net = networks.GraphSage(20, [128] * 3, 4, "pool", 0)
+    ref = sage_ref.GraphSageRef(20, [128] * 3, 4)
+    ref.load_state_dict(net.state_dict())
+    net.to(cuda_dev).eval()
+    with torch.no_grad():
+        logits = net(bg.to(cuda_dev), feats.to(cuda_dev))
+        rl = ref(csr, feats)
+    assert _rel(logits.cpu(), rl) < 1e-4
+    agree = (logits.argmax(1).cpu() == rl.argmax(1)).float().mean().item()
+    assert agree >= 0.9999
+
+
+@pytest.mark.parametrize("agg", ["mean", "gcn"])
+def test_graphsage_mean_gcn(cuda_dev, agg):
+    bg, feats, labels, csr, (s, d) = _batch([3, 4], isolated=2)
+    torch.manual_seed(3)
+    net = networks.GraphSage(20, [64, 32], 4, agg, 0).to(cuda_dev)
+    x = feats.to(cuda_dev).requires_grad_(True)
+    out = net(bg.to(cuda_dev), x)
+    out.square().sum().backward()
+    # plain-torch restatement of DGL's mean / gcn aggregators
+    N = feats.shape[0]
+    deg = torch.bincount(d, minlength=N).double().view(-1, 1)
+    h = feats.double().requires_grad_(True)
+    hh = h
+    params = {k: v.detach().cpu().double().requires_grad_(True) for k, v in net.named_parameters()}
+    for i in range(3):
+        summed = torch.zeros(N, hh.shape[1], dtype=torch.float64).index_add(0, d, hh[s])
+        Wn, bn = params[f"layers.{i}.fc_neigh.weight"], params[f"layers.{i}.fc_neigh.bias"]
+        if agg == "mean":
+            neigh = torch.where(deg > 0, summed / deg.clamp(min=1), torch.zeros_like(summed))
+            o = hh @ params[f"layers.{i}.fc_self.weight"].T + params[f"layers.{i}.fc_self.bias"] + neigh @ Wn.T + bn
+        else:
+            o = ((summed + hh) / (deg + 1)) @ Wn.T + bn
+        hh = torch.relu(o) if i < 2 else o
+    hh.square().sum().backward()
+    assert _rel(out.detach().cpu(), hh.detach()) < 1e-4
+    assert _rel_norm(x.grad.cpu(), h.grad) < 1e-4
+    for k, v in net.named_parameters():
+        assert _rel_norm(v.grad.cpu(), params[k].grad) < 1e-4, k
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3"])
+def test_gat_stack_fwd_bwd(cuda_dev, mode):
+    ops.set_gemm_mode(mode)
+    try:
+        bg, feats, labels, _, (s, d) = _batch([1, 2])
+        torch.manual_seed(4)
+        net = networks.GAT(20, [64, 64, 64], 4, [4, 4, 4], [False, False, True])
+        ref = gat_ref.GATRef(20, [64, 64, 64], 4, [4, 4, 4], [False, False, True])
+        with torch.no_grad():
+            for l in net.layers:
+                l.bias.normal_(std=0.1)
+        ref.load_state_dict(net.state_dict())
+        net.to(cuda_dev)
+        w = torch.tensor([0.1, 1., 2., 2.])
+        x = feats.to(cuda_dev).requires_grad_(True)
+        logits = net(bg.to(cuda_dev), x)
+        loss = ops.weighted_cross_entropy(logits, labels.to(cuda_dev), w.to(cuda_dev))
+        loss.backward()
+        xr = feats.clone().requires_grad_(True)
+        rl = ref((s, d), xr)
+        rloss = F.cross_entropy(rl, labels, weight=w)
+        rloss.backward()
+        assert _rel(logits.detach().cpu(), rl.detach()) < 1e-4
+        _compare_grads(net, ref, 1e-4)
+        assert _rel_norm(x.grad.cpu(), xr.grad) < 1e-4
+    finally:
+        ops.set_gemm_mode("tf32x3")
+
+
+def test_gat_layer_variants(cuda_dev):
+    """residual Linear / Identity, no bias, long rows (> 32 in-edges), H*F = 1024, 1-head F=4 output layer."""
+    ops.set_gemm_mode("fp32")
+    try:
+        rng = np.random.default_rng(0)
+        n = 300
+        src = np.concatenate([np.arange(n), rng.integers(0, n, 4000), rng.integers(0, n, 100)])
+        dst = np.concatenate([np.arange(n), rng.integers(0, n, 4000), np.full(100, 7)])
+        bg = G.from_edge_list(src, dst, n)
+        s, d = bg.edges()
+        for (fin, fo, H, res, act) in [(20, 256, 4, True, F.elu), (1024, 256, 4, True, F.elu), (64, 4, 1, False, None),
+                                       (20, 6, 3, False, F.elu)]:
+            torch.manual_seed(5)
+            layer = networks.GATConv(fin, fo, H, 0, 0, 0.2, res, act)
+            ref = gat_ref.GATConvRef(fin, fo, H, 0.2, res, act)
+            with torch.no_grad():
+                layer.bias.normal_(std=0.1)
+            ref.load_state_dict(layer.state_dict())
+            layer.to(cuda_dev)
+            x0 = torch.randn(n, fin)
+            x = x0.to(cuda_dev).requires_grad_(True)
+            out = layer(bg.to(cuda_dev), x)
+            out.square().sum().backward()
+            xr = x0.clone().requires_grad_(True)
+            ro = ref((s, d), xr)
+            ro.square().sum().backward()
+            assert out.shape == ro.shape
+            assert _rel(out.detach().cpu(), ro.detach()) < 1e-4, (fin, fo, H)
+            assert _rel_norm(x.grad.cpu(), xr.grad) < 1e-4, (fin, fo, H)
+            _compare_grads(layer, ref, 1e-4)
+    finally:
+        ops.set_gemm_mode("tf32x3")
+
+
+def test_gat_zero_in_degree_raises(cuda_dev):
+    from gnn_tumor_seg_b200._lib import GtsError
+    g = synth.make_small_graph(0, n_nodes=50, isolated=2)
+    layer = networks.GATConv(20, 8, 2).to(cuda_dev)
+    with pytest.raises(GtsError, match="0-in-degree"):
+        layer(G.from_edge_list(g.src, g.dst, g.n_nodes).to(cuda_dev), torch.as_tensor(g.features).to(cuda_dev))
+
+
+def test_full_config_7x256_one_graph_inference(cuda_dev):
+    """BASELINE config 1: GraphSAGE-pool 7x256 inference on one 15k-node graph vs the CPU oracle."""
+    g = synth.make_graph(0)
+    torch.manual_seed(0)
+    net = networks.GraphSage(20, [256] * 7, 4, "pool", 0)
+    ref = sage_ref.GraphSageRef(20, [256] * 7, 4)
+    ref.load_state_dict(net.state_dict())
+    net.to(cuda_dev).eval()
+    bg = G.from_edge_list(g.src, g.dst, g.n_nodes).to(cuda_dev)
+    feats = torch.as_tensor(g.features)
+    with torch.no_grad():
+        logits = net(bg, feats.to(cuda_dev)).cpu()
+        indptr, indices = (t.cpu().numpy() for t in bg.csr)
+        rl = ref((indptr, indices), feats)
+    assert _rel(logits, rl) < 1e-4
+    assert (logits.argmax(1) == rl.argmax(1)).float().mean().item() >= 0.9999
