@@ -183,6 +183,14 @@ __global__ void transpose_kernel(const float* __restrict__ in, int64_t ldin, int
   }
 }
 
+void launch_splitk_reduce(const float* partial, int64_t split_stride, int splits, int64_t rows, int64_t cols,
+                          float* C, int64_t ldc, cudaStream_t st) {
+  const int64_t total = rows * cols;
+  int blocks = (int)ceil_div<int64_t>(total, 256);
+  if (blocks < 1) blocks = 1;
+  splitk_reduce_kernel<<<blocks, 256, 0, st>>>(partial, split_stride, splits, rows, cols, C, ldc);
+}
+
 static int colsum_blocks(int64_t rows) {
   int64_t b = ceil_div<int64_t>(rows, 256);
   const int64_t cap = (int64_t)sm_count() * 4;
@@ -301,7 +309,7 @@ int gts_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb,
   }
   GTS_CHECK_ARG(A && B, "gts_gemm_tn: null operand");
   GTS_CHECK_ARG(mode >= GTS_GEMM_FP32 && mode <= GTS_GEMM_TF32X3, "gts_gemm_tn: unknown mode %d", mode);
-  if (mode != GTS_GEMM_FP32 && gemm_tn_tcgen05_supported(A, lda, B, ldb, Mo, No, K))
+  if (mode == GTS_GEMM_TF32 && gemm_tn_tcgen05_supported(A, lda, B, ldb, Mo, No, K))
     return gemm_tn_tcgen05(A, lda, B, ldb, C, ldc, Mo, No, K, mode, workspace, workspace_bytes, st);
   return gemm_tn_simt(A, lda, B, ldb, C, ldc, Mo, No, K, workspace, workspace_bytes, st);
 }

@@ -1,12 +1,491 @@
-// gemm_tcgen05.cu — placeholder until the tcgen05/TMA kernels land: reports
-// every shape as unsupported so gts_gemm_* falls through to the SIMT kernels.
+// gemm_tcgen05.cu — K1/K3/K4 dense contractions on the 5th-gen tensor cores.
+//
+//   tcgen05.mma.cta_group::1.kind::tf32 (M=128, N<=256, K=8 per instruction),
+//   operands staged in shared memory by TMA (cp.async.bulk.tensor, 128B
+//   swizzle), fp32 accumulators in TMEM (two 256-column buffers so the MMA of
+//   tile i+1 overlaps the epilogue of tile i), epilogue read back with
+//   tcgen05.ld and fused bias / ReLU / ReLU-mask.  Persistent CTAs, one per SM.
+//
+// Replaces nn.Linear inside DGL SAGEConv / GATConv and its autograd (invoked at
+// reference model/networks.py:35,63,65):
+//   NT form  C[M,N]  = act(A1 B1^T + A2 B2^T + bias)  — forward and data-gradient
+//                      GEMMs; both operands K-major; the two-source K loop is the
+//                      concatenated fc_self || fc_neigh contraction;
+//   TN form  C[Mo,No] = A^T B over K = nodes          — weight gradients; both
+//                      operands MN-major (TMA boxes of 32 nodes x 32 columns),
+//                      split-K across the grid + deterministic reduction.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 =
+// TMEM allocator + MMA issuer (one elected lane), warps 2..5 = epilogue (each
+// owns the TMEM lane quarter warp_id % 4).
+//
+// Arithmetic modes: GTS_GEMM_TF32 — operands rounded to TF32 by the TMA load
+// (CU_TENSOR_MAP_DATA_TYPE_TFLOAT32), one MMA pass; GTS_GEMM_TF32X3 — see the
+// split kernel variant below (hi/lo split in shared memory, three MMA passes,
+// fp32-accurate).
 #include "common.cuh"
+#include <cuda.h>
+
 namespace gts {
-bool gemm_nt_tcgen05_supported(const gts_gemm_nt_args*) { return false; }
-bool gemm_tn_tcgen05_supported(const float*, int64_t, const float*, int64_t, int32_t, int32_t, int64_t) { return false; }
-size_t gemm_tn_tcgen05_ws(int32_t, int32_t, int64_t, int32_t) { return 0; }
-int gemm_nt_tcgen05(const gts_gemm_nt_args*, cudaStream_t) { set_error("tcgen05 GEMM not built"); return GTS_ERR_UNSUPPORTED; }
-int gemm_tn_tcgen05(const float*, int64_t, const float*, int64_t, float*, int64_t, int32_t, int32_t, int64_t, int32_t, void*, size_t, cudaStream_t) {
-  set_error("tcgen05 GEMM not built"); return GTS_ERR_UNSUPPORTED;
+
+void launch_splitk_reduce(const float* partial, int64_t split_stride, int splits, int64_t rows, int64_t cols,
+                          float* C, int64_t ldc, cudaStream_t st);   // gemm_simt.cu
+
+namespace tc {
+
+constexpr int BM = 128;            // UMMA M
+constexpr int BK = 32;             // fp32 elements per k-block = one 128-byte swizzle span
+constexpr int UMMA_K = 8;          // tf32: 32 bytes per instruction along K
+constexpr int MAX_BN = 256;
+constexpr int A_STAGE_BYTES = BM * BK * 4;        // 16 KB
+constexpr int B_STAGE_BYTES = MAX_BN * BK * 4;    // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int EPI_LD = 36;                        // padded row (floats) of the per-warp staging tile
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;    // 4 epilogue warps
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+
+template <int STAGES>
+struct SmemLayout {
+  static constexpr int stages_bytes = STAGES * STAGE_BYTES;
+  static constexpr int epi_off = stages_bytes;
+  static constexpr int bar_off = epi_off + EPI_BYTES;
+  // full[STAGES], empty[STAGES], split[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
+  static constexpr int total = bar_off + (3 * STAGES + 4) * 8 + 16;
+  static constexpr int dyn_bytes = total + 1024;   // slack for the manual 1024-byte alignment
+};
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) break;
+    if (++spins > (1u << 22)) __trap();    // watchdog: a protocol bug must fault, not hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (SM100 UMMA), version 1.
+//   K-major  (layout 2 = SWIZZLE_128B, 16-byte swizzle granule): LBO unused (1),
+//            SBO = 1024 B between 8-row groups;
+//   MN-major (layout 1 = SWIZZLE_128B_BASE32B — the only MN-major layout the
+//            tensor core accepts for 32-bit (tf32) operands; pairs with the TMA
+//            swizzle CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 32 contiguous
+//            MN elements, 4 k-rows per 512-byte swizzle atom; LBO = bytes between
+//            32-element MN chunks, SBO = 512 B between groups of 4 k-rows.
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;     // descriptor version (Blackwell)
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+// Instruction descriptor: D = f32, A = B = tf32, dense, no negate.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((mn_major ? 1u : 0u) << 15) | ((mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct Params {
+  // common
+  int tiles_m, tiles_n;
+  int BN;                 // UMMA N of this launch (multiple of 16, <= 256)
+  int M, N;               // output extents (NT: rows/cols of C; TN: Mo/No)
+  float* C; int64_t ldc;
+  // NT
+  int kb1, kb2;           // k-blocks of source 1 / 2
+  const float* bias; const float* aux; int64_t ldaux; int act;
+  // TN (split-K)
+  int splits; int kb_per_split; int kb_total; int64_t split_stride;
+};
+
+// ---------------------------------------------------------------------------
+// The kernel.  TN = false: NT form;  TN = true: weight-gradient form.
+// X3 = true: 3xTF32 — four extra "split" warps rewrite each landed stage into
+// hi / lo parts and the MMA warp issues hi*hi + hi*lo + lo*hi.
+// ---------------------------------------------------------------------------
+template <bool TN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, const Params p) {
+  using L = SmemLayout<STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::bar_off);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = full_bar + 3 * STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* epi_stage = reinterpret_cast<float*>(smem + L::epi_off);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&tmA1); prefetch_tmap(&tmB1);
+    if (!TN && p.kb2 > 0) { prefetch_tmap(&tmA2); prefetch_tmap(&tmB2); }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n_work = TN ? p.tiles_m * p.tiles_n * p.splits : p.tiles_m * p.tiles_n;
+  const uint32_t stage_tx_bytes = (uint32_t)(BM + p.BN) * BK * 4;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        int tile = w, split = 0;
+        if (TN) { split = w % p.splits; tile = w / p.splits; }
+        const int m0 = (tile / p.tiles_n) * BM;
+        const int n0 = (tile % p.tiles_n) * p.BN;
+        int kb_beg = 0, kb_end = p.kb1 + p.kb2;
+        if (TN) { kb_beg = split * p.kb_per_split; kb_end = min(p.kb_total, kb_beg + p.kb_per_split); }
+        for (int kb = kb_beg; kb < kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], stage_tx_bytes);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          if (!TN) {
+            const bool second = kb >= p.kb1;
+            const int k0 = (second ? kb - p.kb1 : kb) * BK;
+            tma_load_2d(sa, second ? &tmA2 : &tmA1, &full_bar[stage], k0, m0);
+            tma_load_2d(sb, second ? &tmB2 : &tmB1, &full_bar[stage], k0, n0);
+          } else {
+            const int k0 = kb * BK;    // node rows
+#pragma unroll
+            for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * 4096, &tmA1, &full_bar[stage], m0 + 32 * c, k0);
+            for (int c = 0; c < p.BN / 32; ++c) tma_load_2d(sb + c * 4096, &tmB1, &full_bar[stage], n0 + 32 * c, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BM, p.BN, TN);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        int kb_beg = 0, kb_end = p.kb1 + p.kb2;
+        if (TN) { const int split = w % p.splits; kb_beg = split * p.kb_per_split; kb_end = min(p.kb_total, kb_beg + p.kb_per_split); }
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * MAX_BN;
+        for (int kb = kb_beg; kb < kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            uint64_t da, db;
+            if (!TN) {   // K-major: advance 32 bytes inside the 128-byte swizzle span
+              da = make_smem_desc(sa + k * UMMA_K * 4, 16, 1024, kLayoutSw128);
+              db = make_smem_desc(sb + k * UMMA_K * 4, 16, 1024, kLayoutSw128);
+            } else {     // MN-major: 8 node rows = two 512-byte swizzle atoms per 32-column chunk
+              da = make_smem_desc(sa + k * 1024, 4096, 512, kLayoutSw128Base32);
+              db = make_smem_desc(sb + k * 1024, 4096, 512, kLayoutSw128Base32);
+            }
+            tcgen05_mma_tf32(d_tmem, da, db, idesc, (kb > kb_beg || k > 0) ? 1u : 0u);
+          }
+          tcgen05_commit(&empty_bar[stage]);       // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tcgen05_commit(&tmem_full[acc]);           // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ======================= epilogue warps =======================
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    float* stg = epi_stage + (warp - 2) * 32 * EPI_LD;
+    int it = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      int tile = w, split = 0;
+      if (TN) { split = w % p.splits; tile = w / p.splits; }
+      const int m0 = (tile / p.tiles_n) * BM + q * 32;
+      const int n0 = (tile % p.tiles_n) * p.BN;
+      float* Cout = p.C + (TN ? (int64_t)split * p.split_stride : 0);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t t_base = tmem_base + (uint32_t)acc * MAX_BN + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_base + c0, v);
+        tmem_ld_wait();
+        // lane = row: park the 32 columns of this row in the padded staging tile
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * j) =
+              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                          __uint_as_float(v[4 * j + 3]));
+        __syncwarp();
+        // coalesced write-out: 8 lanes cover one 128-byte row segment, 4 rows per instruction
+        const int cc = (lane & 7) * 4;
+        const int col = n0 + c0 + cc;
+#pragma unroll
+        for (int r = 0; r < 32; r += 4) {
+          const int rr = r + (lane >> 3);
+          const int64_t row = (int64_t)m0 + rr;
+          if (row < p.M && col < p.N && c0 + cc < p.BN) {
+            float4 x = *reinterpret_cast<const float4*>(stg + rr * EPI_LD + cc);
+            if (!TN) {
+              if (p.bias) {
+                const float4 b = *reinterpret_cast<const float4*>(p.bias + col);
+                x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+              }
+              if (p.act == GTS_ACT_RELU) {
+                x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+              } else if (p.act == GTS_ACT_MASK_POS) {
+                const float4 a = ldg_nc_na(reinterpret_cast<const float4*>(p.aux + row * p.ldaux + col));
+                x.x = a.x > 0.f ? x.x : 0.f; x.y = a.y > 0.f ? x.y : 0.f;
+                x.z = a.z > 0.f ? x.z : 0.f; x.w = a.w > 0.f ? x.w : 0.f;
+              }
+            }
+            *reinterpret_cast<float4*>(Cout + row * p.ldc + col) = x;
+          }
+        }
+        __syncwarp();
+      }
+      tcgen05_fence_before();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [rows, cols] with row stride ld (elements); box = box_cols x box_rows.
+static bool encode_2d(CUtensorMap* tm, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+                      bool round_tf32, bool swizzle_atom_32b = false) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return false; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, round_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_atom_32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return false; }
+  return true;
+}
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline bool operand_ok(const float* p, int64_t ld) { return p && al16(p) && ld % 4 == 0 && ld > 0; }
+
+constexpr int kStages = 4;
+
+template <bool TN>
+static int configure_kernel() {
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<TN, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SmemLayout<kStages>::dyn_bytes);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d) failed: %s", SmemLayout<kStages>::dyn_bytes, cudaGetErrorString(e)); return GTS_ERR_CUDA; }
+    done = true;
+  }
+  return GTS_OK;
+}
+
+static int pick_bn(int n, int granule) {
+  int bn = n >= MAX_BN ? MAX_BN : ((n + granule - 1) / granule) * granule;
+  return bn;
+}
+
+}  // namespace tc
+
+bool gemm_nt_tcgen05_supported(const gts_gemm_nt_args* a) {
+  if (a->mode == GTS_GEMM_TF32X3) return false;     // 3xTF32 variant: see gemm_tcgen05_x3 (falls back to SIMT fp32 until built)
+  if (a->M < 1 || a->N < 8 || a->N % 4 != 0) return false;
+  if (a->K1 < 1 || !tc::operand_ok(a->A1, a->lda1) || !tc::operand_ok(a->B1, a->ldb1)) return false;
+  const bool two = a->A2 && a->B2 && a->K2 > 0;
+  if (two && (!tc::operand_ok(a->A2, a->lda2) || !tc::operand_ok(a->B2, a->ldb2))) return false;
+  if (!tc::al16(a->C) || a->ldc % 4 != 0) return false;
+  if (a->bias && !tc::al16(a->bias)) return false;
+  if (a->act == GTS_ACT_MASK_POS && (!tc::al16(a->aux) || a->ldaux % 4 != 0)) return false;
+  return tc::get_encode() != nullptr;
+}
+
+int gemm_nt_tcgen05(const gts_gemm_nt_args* a, cudaStream_t st) {
+  using namespace tc;
+  int rc = configure_kernel<false>();
+  if (rc != GTS_OK) return rc;
+  const bool two = a->A2 && a->B2 && a->K2 > 0;
+  Params p{};
+  p.BN = pick_bn(a->N, 16);
+  p.tiles_m = (a->M + BM - 1) / BM;
+  p.tiles_n = (a->N + p.BN - 1) / p.BN;
+  p.M = a->M; p.N = a->N; p.C = a->C; p.ldc = a->ldc;
+  p.kb1 = (a->K1 + BK - 1) / BK;
+  p.kb2 = two ? (a->K2 + BK - 1) / BK : 0;
+  p.bias = a->bias; p.aux = a->aux; p.ldaux = a->ldaux; p.act = a->act;
+  p.splits = 1;
+  CUtensorMap tA1, tA2, tB1, tB2;
+  if (!encode_2d(&tA1, a->A1, a->M, a->K1, a->lda1, BK, BM, true)) return GTS_ERR_CUDA;
+  if (!encode_2d(&tB1, a->B1, a->N, a->K1, a->ldb1, BK, p.BN, true)) return GTS_ERR_CUDA;
+  if (two) {
+    if (!encode_2d(&tA2, a->A2, a->M, a->K2, a->lda2, BK, BM, true)) return GTS_ERR_CUDA;
+    if (!encode_2d(&tB2, a->B2, a->N, a->K2, a->ldb2, BK, p.BN, true)) return GTS_ERR_CUDA;
+  } else {
+    tA2 = tA1; tB2 = tB1;
+  }
+  const int n_work = p.tiles_m * p.tiles_n;
+  const int grid = n_work < sm_count() ? n_work : sm_count();
+  gemm_tc_kernel<false, kStages><<<grid, NUM_THREADS, SmemLayout<kStages>::dyn_bytes, st>>>(tA1, tA2, tB1, tB2, p);
+  GTS_LAUNCH_CHECK();
+  return GTS_OK;
+}
+
+bool gemm_tn_tcgen05_supported(const float* A, int64_t lda, const float* B, int64_t ldb, int32_t Mo, int32_t No, int64_t K) {
+  if (Mo < 16 || No < 16 || No % 4 != 0 || K < 1 || K > 0x7fffffff) return false;
+  if (!tc::operand_ok(A, lda) || !tc::operand_ok(B, ldb)) return false;
+  return tc::get_encode() != nullptr;
+}
+
+static void tn_plan(int32_t Mo, int32_t No, int64_t K, tc::Params& p) {
+  using namespace tc;
+  p.BN = pick_bn(No, 32);
+  p.tiles_m = (Mo + BM - 1) / BM;
+  p.tiles_n = (No + p.BN - 1) / p.BN;
+  p.kb_total = (int)((K + BK - 1) / BK);
+  const int tiles = p.tiles_m * p.tiles_n;
+  int splits = sm_count() / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.split_stride = (int64_t)Mo * No;
+}
+
+size_t gemm_tn_tcgen05_ws(int32_t Mo, int32_t No, int64_t K, int32_t mode) {
+  (void)mode;
+  if (Mo < 1 || No < 1 || K < 1) return 0;
+  tc::Params p{};
+  tn_plan(Mo, No, K, p);
+  return align_up((size_t)p.splits * (size_t)Mo * (size_t)No * sizeof(float), 256);
+}
+
+int gemm_tn_tcgen05(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                    int32_t Mo, int32_t No, int64_t K, int32_t mode, void* ws, size_t ws_bytes, cudaStream_t st) {
+  using namespace tc;
+  (void)mode;
+  int rc = configure_kernel<true>();
+  if (rc != GTS_OK) return rc;
+  Params p{};
+  tn_plan(Mo, No, K, p);
+  const size_t need = align_up((size_t)p.splits * (size_t)Mo * (size_t)No * sizeof(float), 256);
+  if (!ws || ws_bytes < need) { set_error("gts_gemm_tn: workspace %zu < required %zu", ws_bytes, need); return GTS_ERR_WORKSPACE; }
+  p.M = Mo; p.N = No;
+  p.C = reinterpret_cast<float*>(ws); p.ldc = No;
+  CUtensorMap tA, tB;
+  if (!encode_2d(&tA, A, K, Mo, lda, 32, BK, true, true)) return GTS_ERR_CUDA;
+  if (!encode_2d(&tB, B, K, No, ldb, 32, BK, true, true)) return GTS_ERR_CUDA;
+  const int n_work = p.tiles_m * p.tiles_n * p.splits;
+  const int grid = n_work < sm_count() ? n_work : sm_count();
+  gemm_tc_kernel<true, kStages><<<grid, NUM_THREADS, SmemLayout<kStages>::dyn_bytes, st>>>(tA, tA, tB, tB, p);
+  GTS_LAUNCH_CHECK();
+  launch_splitk_reduce(p.C, p.split_stride, p.splits, Mo, No, C, ldc, st);
+  GTS_LAUNCH_CHECK();
+  return GTS_OK;
+}
+
 }  // namespace gts
