@@ -40,6 +40,17 @@ class GemmNtArgs(C.Structure):
     ]
 
 
+class SageLayer(C.Structure):
+    """struct gts_sage_layer (include/gts.h)."""
+    _fields_ = [("din", C.c_int32), ("dout", C.c_int32), ("relu", C.c_int32), ("reserved", C.c_int32),
+                ("Wp", C.c_void_p), ("bp", C.c_void_p), ("Ws", C.c_void_p), ("Wn", C.c_void_p), ("b", C.c_void_p)]
+
+
+class SageLayerGrads(C.Structure):
+    """struct gts_sage_layer_grads (include/gts.h)."""
+    _fields_ = [("dWp", C.c_void_p), ("dbp", C.c_void_p), ("dWs", C.c_void_p), ("dWn", C.c_void_p), ("db", C.c_void_p)]
+
+
 # name -> (restype, argtypes); mirrors include/gts.h one to one
 _SIGNATURES = {
     "gts_version": (C.c_int, []),
@@ -68,6 +79,12 @@ _SIGNATURES = {
     "gts_segsum_bwd": (C.c_int, [c_f32p, C.c_int64, c_i32p, c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int32,
                                  c_f32p, C.c_int64, c_stream]),
     "gts_mask_pos": (C.c_int, [c_f32p, c_f32p, C.c_int64, c_f32p, c_stream]),
+    "gts_sage_workspace_bytes": (C.c_size_t, [C.POINTER(SageLayer), C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "gts_sage_forward": (C.c_int, [C.POINTER(SageLayer), C.c_int32, c_i32p, c_i32p, C.c_int32, c_f32p, C.c_int64,
+                                   c_f32p, C.c_int64, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, c_stream]),
+    "gts_sage_backward": (C.c_int, [C.POINTER(SageLayer), C.POINTER(SageLayerGrads), C.c_int32, c_i32p, c_i32p,
+                                    C.c_int32, c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_int64,
+                                    C.c_void_p, C.c_size_t, C.c_int32, c_stream]),
     "gts_ce_weighted": (C.c_int, [c_f32p, C.c_int64, c_i64p, c_f32p, C.c_int32, C.c_int32, c_f32p, c_f32p,
                                   C.c_int64, c_stream]),
     "gts_scale_by_inv": (C.c_int, [c_f32p, C.c_int64, C.c_float, c_f32p, c_stream]),

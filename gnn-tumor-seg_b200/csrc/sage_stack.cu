@@ -1,0 +1,204 @@
+// sage_stack.cu — GraphSage.forward / backward over the whole SAGEConv('pool')
+// stack (reference model/networks.py:20-36) as one host call each.  Pure
+// orchestration of the K1/K2/K3 kernels: every launch goes to the caller's
+// stream, all scratch is carved from the caller's workspace.
+#include "common.cuh"
+
+namespace gts {
+
+struct StackPlan {
+  static constexpr int kMaxLayers = 64;
+  int L = 0;
+  int64_t N = 0;
+  size_t neigh[kMaxLayers], arg[kMaxLayers], out[kMaxLayers];
+  size_t P = 0, g0 = 0, g1 = 0, dP = 0, wt0 = 0, wt1 = 0, gemm_ws = 0, colsum_ws = 0;
+  size_t gemm_ws_bytes = 0, colsum_ws_bytes = 0;
+  size_t total = 0;
+};
+
+static bool make_plan(const gts_sage_layer* layers, int L, int64_t N, bool training, int mode, StackPlan& pl) {
+  if (L < 1 || L > StackPlan::kMaxLayers) return false;
+  pl.L = L; pl.N = N;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes ? bytes : 16, 256); return o; };
+  int max_din = 0, max_dim = 0;
+  size_t max_w = 0;
+  for (int l = 0; l < L; ++l) {
+    if (layers[l].din < 1 || layers[l].dout < 1) return false;
+    if (l > 0 && layers[l].din != layers[l - 1].dout) return false;
+    max_din = layers[l].din > max_din ? layers[l].din : max_din;
+    max_dim = layers[l].din > max_dim ? layers[l].din : max_dim;
+    max_dim = layers[l].dout > max_dim ? layers[l].dout : max_dim;
+    size_t w = (size_t)layers[l].din * (size_t)(layers[l].dout > layers[l].din ? layers[l].dout : layers[l].din);
+    max_w = w > max_w ? w : max_w;
+  }
+  const size_t n = (size_t)N;
+  if (training) {
+    for (int l = 0; l < L; ++l) {
+      pl.neigh[l] = take(n * layers[l].din * 4);
+      pl.arg[l] = take(n * layers[l].din * 4);
+      pl.out[l] = (l + 1 < L) ? take(n * layers[l].dout * 4) : 0;
+    }
+    pl.P = take(n * max_din * 4);        // forward: pooled features; backward: dNeigh'
+    pl.g0 = take(n * max_dim * 4);       // backward: dZ / dh ping-pong
+    pl.g1 = take(n * max_dim * 4);
+    pl.dP = take(n * max_din * 4);
+    pl.wt0 = take(max_w * 4);
+    pl.wt1 = take(max_w * 4);
+    size_t gw = 256, cw = 256;
+    for (int l = 0; l < L; ++l) {
+      size_t a = gts_gemm_tn_workspace_bytes(layers[l].dout, layers[l].din, N, mode);
+      size_t b = gts_gemm_tn_workspace_bytes(layers[l].din, layers[l].din, N, mode);
+      gw = a > gw ? a : gw; gw = b > gw ? b : gw;
+      size_t c = gts_colsum_workspace_bytes(N, layers[l].dout), d = gts_colsum_workspace_bytes(N, layers[l].din);
+      cw = c > cw ? c : cw; cw = d > cw ? d : cw;
+    }
+    pl.gemm_ws_bytes = gw; pl.colsum_ws_bytes = cw;
+    pl.gemm_ws = take(gw);
+    pl.colsum_ws = take(cw);
+  } else {
+    pl.P = take(n * max_din * 4);
+    pl.neigh[0] = take(n * max_din * 4);      // single reused neigh buffer
+    pl.g0 = take(n * max_dim * 4);            // activations ping-pong
+    pl.g1 = take(n * max_dim * 4);
+  }
+  pl.total = off;
+  return true;
+}
+
+static inline float* at(void* ws, size_t off) { return reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + off); }
+
+#define GTS_TRY(expr)            \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != GTS_OK) return _rc; \
+  } while (0)
+
+static int nt(const float* A1, int64_t lda1, int K1, const float* B1, int64_t ldb1, const float* A2, int64_t lda2, int K2,
+              const float* B2, int64_t ldb2, const float* bias, int act, const float* aux, int64_t ldaux, float* C,
+              int64_t ldc, int M, int N, int mode, gts_stream_t st) {
+  gts_gemm_nt_args a;
+  a.A1 = A1; a.lda1 = lda1; a.K1 = K1; a.A2 = A2; a.lda2 = lda2; a.K2 = K2;
+  a.B1 = B1; a.ldb1 = ldb1; a.B2 = B2; a.ldb2 = ldb2; a.bias = bias; a.aux = aux; a.ldaux = ldaux;
+  a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.act = act; a.mode = mode;
+  return gts_gemm_nt(&a, st);
+}
+
+}  // namespace gts
+
+using namespace gts;
+
+extern "C" {
+
+size_t gts_sage_workspace_bytes(const gts_sage_layer* layers, int32_t n_layers, int32_t n_nodes,
+                                int32_t training, int32_t mode) {
+  StackPlan pl;
+  if (!layers || n_nodes < 0 || !make_plan(layers, n_layers, n_nodes, training != 0, mode, pl)) return 0;
+  return pl.total;
+}
+
+int gts_sage_forward(const gts_sage_layer* layers, int32_t n_layers,
+                     const int32_t* indptr, const int32_t* indices, int32_t n_nodes,
+                     const float* feats, int64_t ldf, float* logits, int64_t ldl,
+                     void* workspace, size_t workspace_bytes, int32_t training, int32_t mode,
+                     gts_stream_t stream) {
+  GTS_CHECK_ARG(layers && n_layers >= 1, "gts_sage_forward: no layers");
+  GTS_CHECK_ARG(n_nodes >= 0, "gts_sage_forward: negative n_nodes");
+  if (n_nodes == 0) return GTS_OK;
+  GTS_CHECK_ARG(indptr && feats && logits && workspace, "gts_sage_forward: null pointer");
+  StackPlan pl;
+  GTS_CHECK_ARG(make_plan(layers, n_layers, n_nodes, training != 0, mode, pl), "gts_sage_forward: inconsistent layer dims");
+  if (workspace_bytes < pl.total) {
+    set_error("gts_sage_forward: workspace %zu < required %zu", workspace_bytes, pl.total);
+    return GTS_ERR_WORKSPACE;
+  }
+  const int N = n_nodes;
+  const float* h = feats;
+  int64_t ldh = ldf;
+  for (int l = 0; l < n_layers; ++l) {
+    const gts_sage_layer& ly = layers[l];
+    GTS_CHECK_ARG(ly.Wp && ly.bp && ly.Ws && ly.Wn, "gts_sage_forward: layer %d has a null weight", l);
+    float* P = at(workspace, pl.P);
+    GTS_TRY(nt(h, ldh, ly.din, ly.Wp, ly.din, nullptr, 0, 0, nullptr, 0, ly.bp, GTS_ACT_RELU, nullptr, 0, P, ly.din, N,
+               ly.din, mode, stream));
+    float* neigh = at(workspace, training ? pl.neigh[l] : pl.neigh[0]);
+    int32_t* arg = training ? reinterpret_cast<int32_t*>(at(workspace, pl.arg[l])) : nullptr;
+    GTS_TRY(gts_segmax_fwd(P, ly.din, indptr, indices, N, ly.din, neigh, ly.din, arg, ly.din, stream));
+    const bool last = (l + 1 == n_layers);
+    float* out;
+    int64_t ldo;
+    if (last) { out = logits; ldo = ldl; }
+    else if (training) { out = at(workspace, pl.out[l]); ldo = ly.dout; }
+    else { out = at(workspace, (l & 1) ? pl.g1 : pl.g0); ldo = ly.dout; }
+    GTS_TRY(nt(h, ldh, ly.din, ly.Ws, ly.din, neigh, ly.din, ly.din, ly.Wn, ly.din, ly.b,
+               ly.relu ? GTS_ACT_RELU : GTS_ACT_NONE, nullptr, 0, out, ldo, N, ly.dout, mode, stream));
+    h = out; ldh = ldo;
+  }
+  return GTS_OK;
+}
+
+int gts_sage_backward(const gts_sage_layer* layers, const gts_sage_layer_grads* grads, int32_t n_layers,
+                      const int32_t* csc_indptr, const int32_t* csc_indices, int32_t n_nodes,
+                      const float* feats, int64_t ldf, const float* dlogits, int64_t ldd,
+                      float* dfeats, int64_t lddf,
+                      void* workspace, size_t workspace_bytes, int32_t mode, gts_stream_t stream) {
+  GTS_CHECK_ARG(layers && grads && n_layers >= 1, "gts_sage_backward: no layers");
+  GTS_CHECK_ARG(n_nodes >= 0, "gts_sage_backward: negative n_nodes");
+  StackPlan pl;
+  GTS_CHECK_ARG(make_plan(layers, n_layers, n_nodes, true, mode, pl), "gts_sage_backward: inconsistent layer dims");
+  if (n_nodes > 0 && workspace_bytes < pl.total) {
+    set_error("gts_sage_backward: workspace %zu < required %zu", workspace_bytes, pl.total);
+    return GTS_ERR_WORKSPACE;
+  }
+  GTS_CHECK_ARG(n_nodes == 0 || (feats && dlogits && workspace), "gts_sage_backward: null pointer");
+  const int N = n_nodes;
+  const float* dZ = dlogits;
+  int64_t ldz = ldd;
+  int pp = 0;
+  for (int l = n_layers - 1; l >= 0; --l) {
+    const gts_sage_layer& ly = layers[l];
+    const gts_sage_layer_grads& g = grads[l];
+    GTS_CHECK_ARG(g.dWp && g.dbp && g.dWs && g.dWn && g.db, "gts_sage_backward: layer %d has a null gradient pointer", l);
+    const float* h = (l == 0) ? feats : at(workspace, pl.out[l - 1]);
+    const int64_t ldh = (l == 0) ? ldf : ly.din;
+    const float* neigh = at(workspace, pl.neigh[l]);
+    const int32_t* arg = reinterpret_cast<const int32_t*>(at(workspace, pl.arg[l]));
+    void* gws = at(workspace, pl.gemm_ws);
+    void* cws = at(workspace, pl.colsum_ws);
+    // (dZ already carries this layer's ReLU mask: the consumer's epilogue applied (out > 0))
+    GTS_TRY(gts_colsum(dZ, ldz, N, ly.dout, g.db, cws, pl.colsum_ws_bytes, stream));
+    GTS_TRY(gts_gemm_tn(dZ, ldz, h, ldh, g.dWs, ly.din, ly.dout, ly.din, N, mode, gws, pl.gemm_ws_bytes, stream));
+    GTS_TRY(gts_gemm_tn(dZ, ldz, neigh, ly.din, g.dWn, ly.din, ly.dout, ly.din, N, mode, gws, pl.gemm_ws_bytes, stream));
+    // dNeigh' = (dZ Wn) * (neigh > 0)
+    float* WnT = at(workspace, pl.wt0);
+    GTS_TRY(gts_transpose(ly.Wn, ly.din, ly.dout, ly.din, WnT, ly.dout, stream));
+    float* dNeigh = at(workspace, pl.P);
+    GTS_TRY(nt(dZ, ldz, ly.dout, WnT, ly.dout, nullptr, 0, 0, nullptr, 0, nullptr, GTS_ACT_MASK_POS, neigh, ly.din, dNeigh,
+               ly.din, N, ly.din, mode, stream));
+    float* dP = at(workspace, pl.dP);
+    if (csc_indptr && csc_indices)
+      GTS_TRY(gts_segmax_bwd_det(dNeigh, ly.din, arg, ly.din, csc_indptr, csc_indices, N, ly.din, dP, ly.din, stream));
+    else
+      GTS_TRY(gts_segmax_bwd(dNeigh, ly.din, arg, ly.din, N, ly.din, dP, ly.din, N, stream));
+    GTS_TRY(gts_gemm_tn(dP, ly.din, h, ldh, g.dWp, ly.din, ly.din, ly.din, N, mode, gws, pl.gemm_ws_bytes, stream));
+    GTS_TRY(gts_colsum(dP, ly.din, N, ly.din, g.dbp, cws, pl.colsum_ws_bytes, stream));
+    if (l > 0 || dfeats) {
+      float* WsT = at(workspace, pl.wt0);
+      float* WpT = at(workspace, pl.wt1);
+      GTS_TRY(gts_transpose(ly.Ws, ly.din, ly.dout, ly.din, WsT, ly.dout, stream));
+      GTS_TRY(gts_transpose(ly.Wp, ly.din, ly.din, ly.din, WpT, ly.din, stream));
+      float* dh;
+      int64_t lddh;
+      if (l == 0) { dh = dfeats; lddh = lddf; }
+      else { dh = at(workspace, pp ? pl.g1 : pl.g0); lddh = ly.din; }
+      // dh = (dZ Ws + dP' Wp) * (h > 0): h is the ReLU output of layer l-1 (no mask for the input features)
+      const bool mask = l > 0 && layers[l - 1].relu != 0;
+      GTS_TRY(nt(dZ, ldz, ly.dout, WsT, ly.dout, dP, ly.din, ly.din, WpT, ly.din, nullptr,
+                 mask ? GTS_ACT_MASK_POS : GTS_ACT_NONE, mask ? h : nullptr, ldh, dh, lddh, N, ly.din, mode, stream));
+      dZ = dh; ldz = lddh; pp ^= 1;
+    }
+  }
+  return GTS_OK;
+}
+
+}  // extern "C"

@@ -45,6 +45,20 @@ def deterministic_backward() -> bool:
     return _deterministic
 
 
+_stack_path = os.environ.get("GTS_STACK_PATH", "1") == "1"
+
+
+def set_stack_path(flag: bool) -> None:
+    """True (default): GraphSage.forward runs the whole layer stack through
+    gts_sage_forward/backward; False: one autograd Function per layer."""
+    global _stack_path
+    _stack_path = bool(flag)
+
+
+def use_stack_path() -> bool:
+    return _stack_path
+
+
 # counts kernels launched through this module (bench.py's gpu_launches claim)
 launch_counter = {"n": 0}
 
@@ -394,6 +408,66 @@ class SagePoolLayerFn(torch.autograd.Function):
 def sage_pool_layer(h, Wp, bp, Ws, Wn, b, graph, relu_out, input_is_relu=False, grad_premasked=False,
                     deterministic=False):
     return SagePoolLayerFn.apply(h, Wp, bp, Ws, Wn, b, graph, relu_out, input_is_relu, grad_premasked, deterministic)
+
+
+class SageStackFn(torch.autograd.Function):
+    """GraphSage.forward over ALL SAGEConv('pool') layers as one libgts call, and the
+    whole backward as another (gts_sage_forward / gts_sage_backward): no Python between
+    the ~20 kernels of a layer.  ``flat`` = (Wp, bp, Ws, Wn, b) per layer; ``relus`` =
+    per-layer ReLU flags."""
+
+    @staticmethod
+    def forward(ctx, graph, feats, relus, deterministic, *flat):
+        require_cuda(feats, *flat)
+        lib = _lib.load()
+        L = len(relus)
+        assert len(flat) == 5 * L
+        feats = _row_major_2d(feats)
+        N = feats.shape[0]
+        dev = feats.device
+        flat = tuple(_f32c(t) for t in flat)
+        layers = (_lib.SageLayer * L)()
+        for l in range(L):
+            Wp, bp, Ws, Wn, b = flat[5 * l:5 * l + 5]
+            layers[l].din, layers[l].dout, layers[l].relu = Ws.shape[1], Ws.shape[0], int(bool(relus[l]))
+            layers[l].Wp, layers[l].bp, layers[l].Ws, layers[l].Wn, layers[l].b = ptr(Wp), ptr(bp), ptr(Ws), ptr(Wn), ptr(b)
+        training = any(ctx.needs_input_grad)
+        mode = _gemm_mode
+        ws = _workspace(lib.gts_sage_workspace_bytes(layers, L, N, int(training), mode), dev)
+        indptr, indices = graph.csr
+        logits = torch.empty((N, flat[5 * (L - 1) + 2].shape[0]), dtype=torch.float32, device=dev)
+        check(lib.gts_sage_forward(layers, L, ptr(indptr), ptr(indices), N, ptr(feats), _ld(feats), ptr(logits),
+                                   logits.shape[1], ptr(ws), ws.numel(), int(training), mode, stream_ptr()),
+              "gts_sage_forward")
+        _count(3 * L)
+        if training:
+            ctx.save_for_backward(feats, ws, *flat)
+            ctx.layers, ctx.graph, ctx.mode, ctx.deterministic = layers, graph, mode, deterministic
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        lib = _lib.load()
+        feats, ws, *flat = ctx.saved_tensors
+        layers, graph = ctx.layers, ctx.graph
+        L = len(layers)
+        N = feats.shape[0]
+        dlogits = _row_major_2d(dlogits)
+        grads = (_lib.SageLayerGrads * L)()
+        outs = []
+        for l in range(L):
+            g5 = [torch.empty_like(t) for t in flat[5 * l:5 * l + 5]]
+            outs.extend(g5)
+            grads[l].dWp, grads[l].dbp, grads[l].dWs, grads[l].dWn, grads[l].db = (ptr(t) for t in g5)
+        dfeats = torch.empty_like(feats) if ctx.needs_input_grad[1] else None
+        cptr = cidx = None
+        if ctx.deterministic:
+            cptr, cidx, _ = graph.csc
+        check(lib.gts_sage_backward(layers, grads, L, ptr(cptr), ptr(cidx), N, ptr(feats), _ld(feats),
+                                    ptr(dlogits), _ld(dlogits), ptr(dfeats), (feats.shape[1] if dfeats is not None else 0),
+                                    ptr(ws), ws.numel(), ctx.mode, stream_ptr()), "gts_sage_backward")
+        _count(20 * L)
+        return (None, dfeats, None, None, *outs)
 
 
 class SageSumLayerFn(torch.autograd.Function):

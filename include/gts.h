@@ -175,6 +175,44 @@ GTS_API int gts_segsum_bwd(const float* dOut, int64_t ldd, const int32_t* csc_in
 GTS_API int gts_mask_pos(const float* grad, const float* ref, int64_t n, float* out, gts_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * Whole-stack entry points: GraphSage.forward over all SAGEConv('pool') layers
+ * (model/networks.py:32-36) and its backward, as ONE host call each, so the
+ * per-layer kernels are enqueued back to back without returning to Python.
+ * Layer l: P = relu(h Wp^T + bp); neigh = segmax(P); out = act(h Ws^T + neigh Wn^T + b),
+ * act = ReLU when relu != 0.  All pointers are device pointers; weights use
+ * the nn.Linear layout [out,in]; b is the effective output bias.
+ * ------------------------------------------------------------------------ */
+typedef struct gts_sage_layer {
+  int32_t din; int32_t dout; int32_t relu; int32_t reserved;
+  const float* Wp; const float* bp; const float* Ws; const float* Wn; const float* b;
+} gts_sage_layer;
+
+typedef struct gts_sage_layer_grads {
+  float* dWp; float* dbp; float* dWs; float* dWn; float* db;
+} gts_sage_layer_grads;
+
+/* Workspace for n_nodes nodes.  training != 0 keeps every layer's neigh /
+ * arg-max / output for the backward; the same buffer must then be handed,
+ * untouched, to gts_sage_backward. */
+GTS_API size_t gts_sage_workspace_bytes(const gts_sage_layer* layers, int32_t n_layers, int32_t n_nodes,
+                                int32_t training, int32_t mode);
+
+GTS_API int gts_sage_forward(const gts_sage_layer* layers, int32_t n_layers,
+                     const int32_t* indptr, const int32_t* indices, int32_t n_nodes,
+                     const float* feats, int64_t ldf, float* logits, int64_t ldl,
+                     void* workspace, size_t workspace_bytes, int32_t training, int32_t mode,
+                     gts_stream_t stream);
+
+/* dlogits [n_nodes, dout_last] (ldd).  csc_indptr/csc_indices non-NULL selects
+ * the deterministic arg-max backward.  dfeats (nullable): gradient w.r.t. the
+ * input features.  dlogits is not modified. */
+GTS_API int gts_sage_backward(const gts_sage_layer* layers, const gts_sage_layer_grads* grads, int32_t n_layers,
+                      const int32_t* csc_indptr, const int32_t* csc_indices, int32_t n_nodes,
+                      const float* feats, int64_t ldf, const float* dlogits, int64_t ldd,
+                      float* dfeats, int64_t lddf,
+                      void* workspace, size_t workspace_bytes, int32_t mode, gts_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * K8 — weighted-mean cross entropy (model/gnn_model.py:30,42).
  * ------------------------------------------------------------------------ */
 
