@@ -309,7 +309,7 @@ int gts_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb,
   }
   GTS_CHECK_ARG(A && B, "gts_gemm_tn: null operand");
   GTS_CHECK_ARG(mode >= GTS_GEMM_FP32 && mode <= GTS_GEMM_TF32X3, "gts_gemm_tn: unknown mode %d", mode);
-  if (mode == GTS_GEMM_TF32 && gemm_tn_tcgen05_supported(A, lda, B, ldb, Mo, No, K))
+  if (mode != GTS_GEMM_FP32 && gemm_tn_tcgen05_supported(A, lda, B, ldb, Mo, No, K))
     return gemm_tn_tcgen05(A, lda, B, ldb, C, ldc, Mo, No, K, mode, workspace, workspace_bytes, st);
   return gemm_tn_simt(A, lda, B, ldb, C, ldc, Mo, No, K, workspace, workspace_bytes, st);
 }

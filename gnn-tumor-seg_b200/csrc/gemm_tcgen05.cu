@@ -25,6 +25,7 @@
 // fp32-accurate).
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace gts {
 
@@ -39,20 +40,28 @@ constexpr int UMMA_K = 8;          // tf32: 32 bytes per instruction along K
 constexpr int MAX_BN = 256;
 constexpr int A_STAGE_BYTES = BM * BK * 4;        // 16 KB
 constexpr int B_STAGE_BYTES = MAX_BN * BK * 4;    // 32 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int OPER_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;   // one set of operands (A | B)
 constexpr int EPI_LD = 36;                        // padded row (floats) of the per-warp staging tile
-constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;    // 4 epilogue warps
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;                  // 10 warps, see roles below
 constexpr int TMEM_COLS = 512;
 
-template <int STAGES>
-struct SmemLayout {
+// X3 = false: 3 stages of (A | B), 8 epilogue warps.
+// X3 = true : 2 stages of (A | B | A_lo | B_lo), 4 epilogue warps + 4 split warps.
+template <bool X3>
+struct Cfg {
+  static constexpr int STAGES = X3 ? 2 : 3;
+  static constexpr int STAGE_BYTES = X3 ? 2 * OPER_BYTES : OPER_BYTES;
+  static constexpr int EPI_WARPS = X3 ? 4 : 8;
+  static constexpr int SPLIT_WARPS = X3 ? 4 : 0;
   static constexpr int stages_bytes = STAGES * STAGE_BYTES;
   static constexpr int epi_off = stages_bytes;
-  static constexpr int bar_off = epi_off + EPI_BYTES;
+  static constexpr int epi_bytes = EPI_WARPS * 32 * EPI_LD * 4;
+  static constexpr int bar_off = epi_off + epi_bytes;
   // full[STAGES], empty[STAGES], split[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
   static constexpr int total = bar_off + (3 * STAGES + 4) * 8 + 16;
   static constexpr int dyn_bytes = total + 1024;   // slack for the manual 1024-byte alignment
+  static_assert(dyn_bytes <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
+  static_assert(2 + EPI_WARPS + SPLIT_WARPS == NUM_THREADS / 32, "warp roles must cover the CTA");
 };
 
 // ---------------------------------------------------------------------------
@@ -157,18 +166,28 @@ struct Params {
 
 // ---------------------------------------------------------------------------
 // The kernel.  TN = false: NT form;  TN = true: weight-gradient form.
-// X3 = true: 3xTF32 — four extra "split" warps rewrite each landed stage into
-// hi / lo parts and the MMA warp issues hi*hi + hi*lo + lo*hi.
+// X3 = true: 3xTF32.  The tensor core TRUNCATES fp32 operands to TF32 (measured
+// on B200: a FLOAT32 tensor map reproduces the truncated-operand product to
+// 1e-6), so the landed fp32 tile itself serves as the "hi" part; four split
+// warps write lo = x - trunc(x) next to it and the MMA warp issues
+// lo*hi + hi*lo + hi*hi into the same fp32 TMEM accumulator.
 // ---------------------------------------------------------------------------
-template <bool TN, int STAGES>
+__device__ __forceinline__ float tf32_lo(float x) {
+  return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+}
+
+template <bool TN, bool X3>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, const Params p) {
-  using L = SmemLayout<STAGES>;
+  using L = Cfg<X3>;
+  constexpr int STAGES = L::STAGES;
+  constexpr int STAGE_BYTES = L::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::bar_off);
   uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* split_bar = full_bar + 2 * STAGES;
   uint64_t* tmem_full = full_bar + 3 * STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
@@ -178,8 +197,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+      mbar_init(&split_bar[s], L::SPLIT_WARPS * 32);
+    }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], L::EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(&tmA1); prefetch_tmap(&tmB1);
     if (!TN && p.kb2 > 0) { prefetch_tmap(&tmA2); prefetch_tmap(&tmB2); }
@@ -242,21 +265,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * MAX_BN;
         for (int kb = kb_beg; kb < kb_end; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(X3 ? &split_bar[stage] : &full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            uint64_t da, db;
-            if (!TN) {   // K-major: advance 32 bytes inside the 128-byte swizzle span
-              da = make_smem_desc(sa + k * UMMA_K * 4, 16, 1024, kLayoutSw128);
-              db = make_smem_desc(sb + k * UMMA_K * 4, 16, 1024, kLayoutSw128);
-            } else {     // MN-major: 8 node rows = two 512-byte swizzle atoms per 32-column chunk
-              da = make_smem_desc(sa + k * 1024, 4096, 512, kLayoutSw128Base32);
-              db = make_smem_desc(sb + k * 1024, 4096, 512, kLayoutSw128Base32);
+            // K-major: advance 32 bytes inside the 128-byte swizzle span;
+            // MN-major: 8 node rows = two 512-byte swizzle atoms per 32-column chunk
+            const uint32_t koff = TN ? k * 1024 : k * UMMA_K * 4;
+            const uint32_t lbo = TN ? 4096 : 16, sbo = TN ? 512 : 1024;
+            const uint32_t lay = TN ? kLayoutSw128Base32 : kLayoutSw128;
+            const uint64_t da = make_smem_desc(sa + koff, lbo, sbo, lay);
+            const uint64_t db = make_smem_desc(sb + koff, lbo, sbo, lay);
+            const uint32_t first = (kb > kb_beg || k > 0) ? 1u : 0u;
+            if (X3) {
+              const uint64_t da_lo = make_smem_desc(sa + OPER_BYTES + koff, lbo, sbo, lay);
+              const uint64_t db_lo = make_smem_desc(sb + OPER_BYTES + koff, lbo, sbo, lay);
+              tcgen05_mma_tf32(d_tmem, da_lo, db, idesc, first);   // lo * hi
+              tcgen05_mma_tf32(d_tmem, da, db_lo, idesc, 1u);      // hi * lo
+              tcgen05_mma_tf32(d_tmem, da, db, idesc, 1u);         // hi * hi
+            } else {
+              tcgen05_mma_tf32(d_tmem, da, db, idesc, first);
             }
-            tcgen05_mma_tf32(d_tmem, da, db, idesc, (kb > kb_beg || k > 0) ? 1u : 0u);
           }
           tcgen05_commit(&empty_bar[stage]);       // smem slot reusable once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -264,10 +295,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         tcgen05_commit(&tmem_full[acc]);           // accumulator complete -> epilogue
       }
     }
-  } else {
+  } else if (warp < 2 + L::EPI_WARPS) {
     // ======================= epilogue warps =======================
+    const int ew = warp - 2;
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
-    float* stg = epi_stage + (warp - 2) * 32 * EPI_LD;
+    const int n_col_groups = L::EPI_WARPS / 4;     // warps sharing a lane quarter split the column chunks
+    const int col_group = ew >> 2;
+    float* stg = epi_stage + ew * 32 * EPI_LD;
+    const int cc = (lane & 7) * 4;
+    const int rsub = lane >> 3;
+    const bool masked = !TN && p.act == GTS_ACT_MASK_POS;
     int it = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -277,12 +314,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const int m0 = (tile / p.tiles_n) * BM + q * 32;
       const int n0 = (tile % p.tiles_n) * p.BN;
       float* Cout = p.C + (TN ? (int64_t)split * p.split_stride : 0);
+      const uint32_t t_base = tmem_base + (uint32_t)acc * MAX_BN + ((uint32_t)(q * 32) << 16);
+
+      // ReLU-mask source: fetched one chunk ahead so its latency hides behind the TMEM load
+      float4 aux_cur[8], aux_nxt[8];
+      auto load_aux = [&](int c0, float4 (&dst)[8]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int64_t row = (int64_t)m0 + 4 * j + rsub;
+          const int col = n0 + c0 + cc;
+          dst[j] = (row < p.M && col < p.N && c0 + cc < p.BN)
+                       ? ldg_nc_na(reinterpret_cast<const float4*>(p.aux + row * p.ldaux + col))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      const int c_first = col_group * 32, c_step = n_col_groups * 32;
+      if (masked && c_first < p.BN) load_aux(c_first, aux_cur);
+
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      const uint32_t t_base = tmem_base + (uint32_t)acc * MAX_BN + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      for (int c0 = c_first; c0 < p.BN; c0 += c_step) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_base + c0, v);
+        if (masked && c0 + c_step < p.BN) load_aux(c0 + c_step, aux_nxt);
         tmem_ld_wait();
         // lane = row: park the 32 columns of this row in the padded staging tile
 #pragma unroll
@@ -292,23 +346,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                           __uint_as_float(v[4 * j + 3]));
         __syncwarp();
         // coalesced write-out: 8 lanes cover one 128-byte row segment, 4 rows per instruction
-        const int cc = (lane & 7) * 4;
         const int col = n0 + c0 + cc;
+        const bool col_ok = col < p.N && c0 + cc < p.BN;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!TN && p.bias && col_ok) b = *reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-        for (int r = 0; r < 32; r += 4) {
-          const int rr = r + (lane >> 3);
+        for (int j = 0; j < 8; ++j) {
+          const int rr = 4 * j + rsub;
           const int64_t row = (int64_t)m0 + rr;
-          if (row < p.M && col < p.N && c0 + cc < p.BN) {
+          if (row < p.M && col_ok) {
             float4 x = *reinterpret_cast<const float4*>(stg + rr * EPI_LD + cc);
             if (!TN) {
-              if (p.bias) {
-                const float4 b = *reinterpret_cast<const float4*>(p.bias + col);
-                x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
-              }
+              x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
               if (p.act == GTS_ACT_RELU) {
                 x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
-              } else if (p.act == GTS_ACT_MASK_POS) {
-                const float4 a = ldg_nc_na(reinterpret_cast<const float4*>(p.aux + row * p.ldaux + col));
+              } else if (masked) {
+                const float4 a = aux_cur[j];
                 x.x = a.x > 0.f ? x.x : 0.f; x.y = a.y > 0.f ? x.y : 0.f;
                 x.z = a.z > 0.f ? x.z : 0.f; x.w = a.w > 0.f ? x.w : 0.f;
               }
@@ -317,9 +370,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           }
         }
         __syncwarp();
+        if (masked) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) aux_cur[j] = aux_nxt[j];
+        }
       }
       tcgen05_fence_before();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  } else if (X3) {
+    // ======================= split warps (3xTF32) =======================
+    const int t = threadIdx.x - (2 + L::EPI_WARPS) * 32;          // 0..127
+    const int n_vec = (A_STAGE_BYTES + p.BN * BK * 4) / 16;       // float4 count of (A | used part of B)
+    int stage = 0; uint32_t phase = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      int kb_beg = 0, kb_end = p.kb1 + p.kb2;
+      if (TN) { const int split = w % p.splits; kb_beg = split * p.kb_per_split; kb_end = min(p.kb_total, kb_beg + p.kb_per_split); }
+      for (int kb = kb_beg; kb < kb_end; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        float4* hi = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES + OPER_BYTES);
+#pragma unroll 4
+        for (int i = t; i < n_vec; i += L::SPLIT_WARPS * 32) {
+          const float4 x = hi[i];
+          lo[i] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+        mbar_arrive(&split_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
     }
   }
 
@@ -361,6 +440,8 @@ static bool encode_2d(CUtensorMap* tm, const float* base, int64_t rows, int64_t 
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
+  static const bool no_round = getenv("GTS_TMA_NO_ROUND") != nullptr;
+  if (no_round) round_tf32 = false;
   CUresult r = enc(tm, round_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                    const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swizzle_atom_32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
@@ -372,17 +453,26 @@ static bool encode_2d(CUtensorMap* tm, const float* base, int64_t rows, int64_t 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline bool operand_ok(const float* p, int64_t ld) { return p && al16(p) && ld % 4 == 0 && ld > 0; }
 
-constexpr int kStages = 4;
-
-template <bool TN>
+template <bool TN, bool X3>
 static int configure_kernel() {
   static bool done = false;
   if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<TN, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         SmemLayout<kStages>::dyn_bytes);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d) failed: %s", SmemLayout<kStages>::dyn_bytes, cudaGetErrorString(e)); return GTS_ERR_CUDA; }
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<TN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg<X3>::dyn_bytes);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d) failed: %s", Cfg<X3>::dyn_bytes, cudaGetErrorString(e)); return GTS_ERR_CUDA; }
     done = true;
   }
+  return GTS_OK;
+}
+
+template <bool TN, bool X3>
+static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1, const CUtensorMap& b2,
+                  const Params& p, int n_work, cudaStream_t st) {
+  int rc = configure_kernel<TN, X3>();
+  if (rc != GTS_OK) return rc;
+  const int grid = n_work < sm_count() ? n_work : sm_count();
+  gemm_tc_kernel<TN, X3><<<grid, NUM_THREADS, Cfg<X3>::dyn_bytes, st>>>(a1, a2, b1, b2, p);
+  GTS_LAUNCH_CHECK();
   return GTS_OK;
 }
 
@@ -394,7 +484,6 @@ static int pick_bn(int n, int granule) {
 }  // namespace tc
 
 bool gemm_nt_tcgen05_supported(const gts_gemm_nt_args* a) {
-  if (a->mode == GTS_GEMM_TF32X3) return false;     // 3xTF32 variant: see gemm_tcgen05_x3 (falls back to SIMT fp32 until built)
   if (a->M < 1 || a->N < 8 || a->N % 4 != 0) return false;
   if (a->K1 < 1 || !tc::operand_ok(a->A1, a->lda1) || !tc::operand_ok(a->B1, a->ldb1)) return false;
   const bool two = a->A2 && a->B2 && a->K2 > 0;
@@ -407,8 +496,8 @@ bool gemm_nt_tcgen05_supported(const gts_gemm_nt_args* a) {
 
 int gemm_nt_tcgen05(const gts_gemm_nt_args* a, cudaStream_t st) {
   using namespace tc;
-  int rc = configure_kernel<false>();
-  if (rc != GTS_OK) return rc;
+  const bool x3 = a->mode == GTS_GEMM_TF32X3;
+  const bool rnd = !x3;      // 1xTF32: TMA rounds to nearest; 3xTF32: raw fp32 (the MMA truncates, lo = x - trunc(x))
   const bool two = a->A2 && a->B2 && a->K2 > 0;
   Params p{};
   p.BN = pick_bn(a->N, 16);
@@ -420,19 +509,17 @@ int gemm_nt_tcgen05(const gts_gemm_nt_args* a, cudaStream_t st) {
   p.bias = a->bias; p.aux = a->aux; p.ldaux = a->ldaux; p.act = a->act;
   p.splits = 1;
   CUtensorMap tA1, tA2, tB1, tB2;
-  if (!encode_2d(&tA1, a->A1, a->M, a->K1, a->lda1, BK, BM, true)) return GTS_ERR_CUDA;
-  if (!encode_2d(&tB1, a->B1, a->N, a->K1, a->ldb1, BK, p.BN, true)) return GTS_ERR_CUDA;
+  if (!encode_2d(&tA1, a->A1, a->M, a->K1, a->lda1, BK, BM, rnd)) return GTS_ERR_CUDA;
+  if (!encode_2d(&tB1, a->B1, a->N, a->K1, a->ldb1, BK, p.BN, rnd)) return GTS_ERR_CUDA;
   if (two) {
-    if (!encode_2d(&tA2, a->A2, a->M, a->K2, a->lda2, BK, BM, true)) return GTS_ERR_CUDA;
-    if (!encode_2d(&tB2, a->B2, a->N, a->K2, a->ldb2, BK, p.BN, true)) return GTS_ERR_CUDA;
+    if (!encode_2d(&tA2, a->A2, a->M, a->K2, a->lda2, BK, BM, rnd)) return GTS_ERR_CUDA;
+    if (!encode_2d(&tB2, a->B2, a->N, a->K2, a->ldb2, BK, p.BN, rnd)) return GTS_ERR_CUDA;
   } else {
     tA2 = tA1; tB2 = tB1;
   }
   const int n_work = p.tiles_m * p.tiles_n;
-  const int grid = n_work < sm_count() ? n_work : sm_count();
-  gemm_tc_kernel<false, kStages><<<grid, NUM_THREADS, SmemLayout<kStages>::dyn_bytes, st>>>(tA1, tA2, tB1, tB2, p);
-  GTS_LAUNCH_CHECK();
-  return GTS_OK;
+  return x3 ? launch<false, true>(tA1, tA2, tB1, tB2, p, n_work, st)
+            : launch<false, false>(tA1, tA2, tB1, tB2, p, n_work, st);
 }
 
 bool gemm_tn_tcgen05_supported(const float* A, int64_t lda, const float* B, int64_t ldb, int32_t Mo, int32_t No, int64_t K) {
@@ -467,9 +554,7 @@ size_t gemm_tn_tcgen05_ws(int32_t Mo, int32_t No, int64_t K, int32_t mode) {
 int gemm_tn_tcgen05(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
                     int32_t Mo, int32_t No, int64_t K, int32_t mode, void* ws, size_t ws_bytes, cudaStream_t st) {
   using namespace tc;
-  (void)mode;
-  int rc = configure_kernel<true>();
-  if (rc != GTS_OK) return rc;
+  const bool x3 = mode == GTS_GEMM_TF32X3;
   Params p{};
   tn_plan(Mo, No, K, p);
   const size_t need = align_up((size_t)p.splits * (size_t)Mo * (size_t)No * sizeof(float), 256);
@@ -477,12 +562,11 @@ int gemm_tn_tcgen05(const float* A, int64_t lda, const float* B, int64_t ldb, fl
   p.M = Mo; p.N = No;
   p.C = reinterpret_cast<float*>(ws); p.ldc = No;
   CUtensorMap tA, tB;
-  if (!encode_2d(&tA, A, K, Mo, lda, 32, BK, true, true)) return GTS_ERR_CUDA;
-  if (!encode_2d(&tB, B, K, No, ldb, 32, BK, true, true)) return GTS_ERR_CUDA;
+  if (!encode_2d(&tA, A, K, Mo, lda, 32, BK, !x3, true)) return GTS_ERR_CUDA;
+  if (!encode_2d(&tB, B, K, No, ldb, 32, BK, !x3, true)) return GTS_ERR_CUDA;
   const int n_work = p.tiles_m * p.tiles_n * p.splits;
-  const int grid = n_work < sm_count() ? n_work : sm_count();
-  gemm_tc_kernel<true, kStages><<<grid, NUM_THREADS, SmemLayout<kStages>::dyn_bytes, st>>>(tA, tA, tB, tB, p);
-  GTS_LAUNCH_CHECK();
+  int rc = x3 ? launch<true, true>(tA, tA, tB, tB, p, n_work, st) : launch<true, false>(tA, tA, tB, tB, p, n_work, st);
+  if (rc != GTS_OK) return rc;
   launch_splitk_reduce(p.C, p.split_stride, p.splits, Mo, No, C, ldc, st);
   GTS_LAUNCH_CHECK();
   return GTS_OK;
