@@ -134,6 +134,82 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int64_t 
   }
 }
 
+// float4 variant: rows*cols % 4 == 0, contiguous C (ldc == cols), 16-byte aligned.
+__global__ void splitk_reduce_vec_kernel(const float4* __restrict__ partial, int64_t split_stride4, int splits,
+                                         int64_t total4, float4* __restrict__ C) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    int z = 0;
+    for (; z + 8 <= splits; z += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = ldg_nc_na(partial + (int64_t)(z + j) * split_stride4 + i);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; }
+    }
+    for (; z < splits; ++z) {
+      const float4 v = ldg_nc_na(partial + (int64_t)z * split_stride4 + i);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    C[i] = s;
+  }
+}
+
+// Column sums, wide fast path (cols % 4 == 0, cols <= 1024, 16-byte aligned rows):
+// block = 256 threads = (cols/4 column groups) x (256/(cols/4) row lanes); float4 loads.
+__global__ void __launch_bounds__(256)
+colsum_partial_vec_kernel(const float* __restrict__ A, int64_t lda, int64_t rows, int cols4, int64_t rows_per_block,
+                          float* __restrict__ partial) {
+  extern __shared__ float4 s_red[];                // [row_lanes][cols4]
+  const int row_lanes = 256 / cols4;
+  const int cg = threadIdx.x % cols4, rl = threadIdx.x / cols4;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rl < row_lanes) {
+    int64_t r = r0 + rl;
+    for (; r + 3 * row_lanes < r1; r += 4 * row_lanes) {
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = ldg_nc_na(reinterpret_cast<const float4*>(A + (r + j * row_lanes) * lda) + cg);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; }
+    }
+    for (; r < r1; r += row_lanes) {
+      const float4 v = ldg_nc_na(reinterpret_cast<const float4*>(A + r * lda) + cg);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    s_red[rl * cols4 + cg] = s;
+  }
+  __syncthreads();
+  if (rl == 0) {
+    for (int j = 1; j < row_lanes; ++j) {
+      const float4 v = s_red[j * cols4 + cg];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    reinterpret_cast<float4*>(partial + (int64_t)blockIdx.x * cols4 * 4)[cg] = s;
+  }
+}
+
+// final: out[c] = sum_b partial[b][c]; one block of 256 threads per 32 columns (8 block-lanes x 32 columns)
+__global__ void __launch_bounds__(256)
+colsum_final_wide_kernel(const float* __restrict__ partial, int n_blocks, int32_t cols, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, by = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float s = 0.f;
+  if (c < cols)
+    for (int b = by; b < n_blocks; b += 8) s += partial[(int64_t)b * cols + c];
+  red[by][cx] = s;
+  __syncthreads();
+  if (by == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][cx];
+    out[c] = t;
+  }
+}
+
 // Column sums, pass 1: block b sums rows [b*rows_per_block, ...) of every column.
 __global__ void colsum_partial_kernel(const float* __restrict__ A, int64_t lda, int64_t rows, int32_t cols,
                                       int64_t rows_per_block, float* __restrict__ partial) {
@@ -186,14 +262,23 @@ __global__ void transpose_kernel(const float* __restrict__ in, int64_t ldin, int
 void launch_splitk_reduce(const float* partial, int64_t split_stride, int splits, int64_t rows, int64_t cols,
                           float* C, int64_t ldc, cudaStream_t st) {
   const int64_t total = rows * cols;
+  const bool vec = ldc == cols && total % 4 == 0 && split_stride % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(partial) & 15u) == 0 && (reinterpret_cast<uintptr_t>(C) & 15u) == 0;
+  if (vec) {
+    int blocks = (int)ceil_div<int64_t>(total / 4, 128);
+    if (blocks < 1) blocks = 1;
+    splitk_reduce_vec_kernel<<<blocks, 128, 0, st>>>(reinterpret_cast<const float4*>(partial), split_stride / 4, splits,
+                                                     total / 4, reinterpret_cast<float4*>(C));
+    return;
+  }
   int blocks = (int)ceil_div<int64_t>(total, 256);
   if (blocks < 1) blocks = 1;
   splitk_reduce_kernel<<<blocks, 256, 0, st>>>(partial, split_stride, splits, rows, cols, C, ldc);
 }
 
 static int colsum_blocks(int64_t rows) {
-  int64_t b = ceil_div<int64_t>(rows, 256);
-  const int64_t cap = (int64_t)sm_count() * 4;
+  int64_t b = ceil_div<int64_t>(rows, 128);
+  const int64_t cap = (int64_t)sm_count() * 8;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;
@@ -338,9 +423,19 @@ int gts_colsum(const float* A, int64_t lda, int64_t rows, int32_t cols, float* o
   const int nb = colsum_blocks(rows);
   const int64_t rpb = ceil_div<int64_t>(rows, nb);
   float* partial = reinterpret_cast<float*>(workspace);
-  colsum_partial_kernel<<<nb, 256, 0, st>>>(A, lda, rows, cols, rpb, partial);
-  GTS_LAUNCH_CHECK();
-  colsum_final_kernel<<<(cols + 127) / 128, 128, 0, st>>>(partial, nb, cols, out);
+  const bool vec = cols % 4 == 0 && cols >= 16 && cols <= 1024 && lda % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15u) == 0 &&
+                   256 % (cols / 4) == 0;
+  if (vec) {
+    const int cols4 = cols / 4;
+    const size_t smem = (size_t)(256 / cols4) * cols4 * sizeof(float4);
+    colsum_partial_vec_kernel<<<nb, 256, smem, st>>>(A, lda, rows, cols4, rpb, partial);
+    GTS_LAUNCH_CHECK();
+    colsum_final_wide_kernel<<<(cols + 31) / 32, 256, 0, st>>>(partial, nb, cols, out);
+  } else {
+    colsum_partial_kernel<<<nb, 256, 0, st>>>(A, lda, rows, cols, rpb, partial);
+    GTS_LAUNCH_CHECK();
+    colsum_final_wide_kernel<<<(cols + 31) / 32, 256, 0, st>>>(partial, nb, cols, out);
+  }
   GTS_LAUNCH_CHECK();
   return GTS_OK;
 }

@@ -484,7 +484,7 @@ static int pick_bn(int n, int granule) {
 }  // namespace tc
 
 bool gemm_nt_tcgen05_supported(const gts_gemm_nt_args* a) {
-  if (a->M < 1 || a->N < 8 || a->N % 4 != 0) return false;
+  if (a->M < 1 || a->N < 4 || a->N % 4 != 0) return false;
   if (a->K1 < 1 || !tc::operand_ok(a->A1, a->lda1) || !tc::operand_ok(a->B1, a->ldb1)) return false;
   const bool two = a->A2 && a->B2 && a->K2 > 0;
   if (two && (!tc::operand_ok(a->A2, a->lda2) || !tc::operand_ok(a->B2, a->ldb2))) return false;
@@ -523,7 +523,7 @@ int gemm_nt_tcgen05(const gts_gemm_nt_args* a, cudaStream_t st) {
 }
 
 bool gemm_tn_tcgen05_supported(const float* A, int64_t lda, const float* B, int64_t ldb, int32_t Mo, int32_t No, int64_t K) {
-  if (Mo < 16 || No < 16 || No % 4 != 0 || K < 1 || K > 0x7fffffff) return false;
+  if (Mo < 4 || Mo % 4 != 0 || No < 4 || No % 4 != 0 || K < 1 || K > 0x7fffffff) return false;
   if (!tc::operand_ok(A, lda) || !tc::operand_ok(B, ldb)) return false;
   return tc::get_encode() != nullptr;
 }

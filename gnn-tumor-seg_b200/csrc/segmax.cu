@@ -12,6 +12,7 @@
 // 4*(N*D read + N*D write + N*D argmax + (N+1) + E).
 #include "common.cuh"
 #include <cfloat>
+#include <cstdlib>
 
 namespace gts {
 
@@ -26,22 +27,29 @@ __device__ __forceinline__ void fold_max(float4& best, int4& arg, const float4& 
 
 // LPN lanes per node (power of two <= 32), VEC float4 chunks per lane:
 // covers D4 = D/4 <= LPN*VEC.
-template <int LPN, int VEC, bool WRITE_ARG>
-__global__ void __launch_bounds__(kSegThreads)
+// Work distribution: each CTA owns ONE contiguous range of nodes_per_cta destination
+// nodes and walks it with all its warps side by side.  Supervoxel ids are spatially
+// coherent (SLIC numbers its clusters in raster order), so the neighbour rows of
+// consecutive nodes overlap heavily: keeping an SM on one sliding window of ids turns
+// most of the E x D gather traffic into L1 hits instead of L2 round trips.
+template <int LPN, int VEC, bool WRITE_ARG, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 segmax_fwd_vec_kernel(const float* __restrict__ P, int64_t ldp, const int32_t* __restrict__ indptr,
                       const int32_t* __restrict__ indices, int32_t N, int32_t D4,
-                      float* __restrict__ neigh, int64_t ldn, int32_t* __restrict__ argmax, int64_t ldarg) {
+                      float* __restrict__ neigh, int64_t ldn, int32_t* __restrict__ argmax, int64_t ldarg,
+                      int64_t nodes_per_cta) {
   constexpr int NPW = 32 / LPN;   // nodes per warp
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPN;
   const int slot = lane / LPN;
   const unsigned full = 0xffffffffu;
-  const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t v_begin = (int64_t)blockIdx.x * nodes_per_cta;
+  const int64_t v_end = v_begin + nodes_per_cta < N ? v_begin + nodes_per_cta : N;
+  const int64_t warp_stride = (int64_t)(THREADS / 32) * NPW;
 
-  for (int64_t v0 = warp_global * NPW; v0 < N; v0 += n_warps * NPW) {
+  for (int64_t v0 = v_begin + (int64_t)(threadIdx.x >> 5) * NPW; v0 < v_end; v0 += warp_stride) {
     const int64_t v = v0 + slot;
-    const bool live = v < N;
+    const bool live = v < v_end;
     int32_t beg = 0, end = 0;
     if (live) { beg = indptr[v]; end = indptr[v + 1]; }
     float4 best[VEC];
@@ -103,6 +111,97 @@ segmax_fwd_vec_kernel(const float* __restrict__ P, int64_t ldp, const int32_t* _
       }
     }
   }
+}
+
+
+// Wide rows with D == 128 * VEC exactly (the 256-wide hidden layers): one warp per
+// destination node, lane l owns float4 chunks l, l+32, ....  The first version of this
+// kernel was ISSUE-bound, not memory-bound (ncu: ~29 SASS instructions per 128-bit load,
+// most of them predicate bookkeeping), so this form keeps the inner loop branch-free:
+// whole groups of four neighbours with no per-neighbour or per-column predicates, the
+// (< 4) remainder handled once per row.  One 768-thread CTA per SM on a contiguous id
+// range keeps the L1 hit rate of the gathers at ~65 % (see the note above).
+template <int VEC, bool WRITE_ARG, int kWideWarps>
+__global__ void __launch_bounds__(kWideWarps * 32, 1)
+segmax_fwd_wide_kernel(const float* __restrict__ P, int64_t ldp, const int32_t* __restrict__ indptr,
+                       const int32_t* __restrict__ indices, int32_t N,
+                       float* __restrict__ neigh, int64_t ldn, int32_t* __restrict__ argmax, int64_t ldarg,
+                       int64_t nodes_per_cta) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const unsigned full = 0xffffffffu;
+  const int64_t v_begin = (int64_t)blockIdx.x * nodes_per_cta;
+  const int64_t v_end = v_begin + nodes_per_cta < N ? v_begin + nodes_per_cta : N;
+  const int slab4 = blockIdx.y * 32 * VEC;       // gridDim.y column slabs of 128*VEC floats each
+  const float4* __restrict__ Pl = reinterpret_cast<const float4*>(P) + slab4 + lane;
+  const uint32_t ld4 = (uint32_t)(ldp >> 2);     // host guarantees N * ld4 < 2^31: 32-bit row offsets
+
+  for (int64_t v = v_begin + warp; v < v_end; v += kWideWarps) {
+    const int32_t beg = indptr[v], end = indptr[v + 1];
+    float4 best[VEC];
+    int4 arg[VEC];
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+      best[c] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      arg[c] = make_int4(-1, -1, -1, -1);
+    }
+    for (int32_t base = beg; base < end; base += 32) {
+      const int32_t my_idx = (base + lane < end) ? indices[base + lane] : 0;
+      const int32_t cnt = min(32, end - base);
+      int32_t j = 0;
+      for (; j + 4 <= cnt; j += 4) {
+        const int32_t u0 = __shfl_sync(full, my_idx, j), u1 = __shfl_sync(full, my_idx, j + 1);
+        const int32_t u2 = __shfl_sync(full, my_idx, j + 2), u3 = __shfl_sync(full, my_idx, j + 3);
+        const float4* p0 = Pl + (uint32_t)u0 * ld4;
+        const float4* p1 = Pl + (uint32_t)u1 * ld4;
+        const float4* p2 = Pl + (uint32_t)u2 * ld4;
+        const float4* p3 = Pl + (uint32_t)u3 * ld4;
+        float4 r0[VEC], r1[VEC], r2[VEC], r3[VEC];
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) { r0[c] = ldg_nc(p0 + 32 * c); r1[c] = ldg_nc(p1 + 32 * c); }
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) { r2[c] = ldg_nc(p2 + 32 * c); r3[c] = ldg_nc(p3 + 32 * c); }
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+          fold_max(best[c], arg[c], r0[c], u0);
+          fold_max(best[c], arg[c], r1[c], u1);
+          fold_max(best[c], arg[c], r2[c], u2);
+          fold_max(best[c], arg[c], r3[c], u3);
+        }
+      }
+      for (; j < cnt; ++j) {
+        const int32_t u0 = __shfl_sync(full, my_idx, j);
+        const float4* p0 = Pl + (uint32_t)u0 * ld4;
+        float4 r0[VEC];
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) r0[c] = ldg_nc(p0 + 32 * c);
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) fold_max(best[c], arg[c], r0[c], u0);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+      float4 o = best[c];
+      if (end == beg) o = make_float4(0.f, 0.f, 0.f, 0.f);     // no in-edges: DGL fills 0
+      stg_na(reinterpret_cast<float4*>(neigh + v * ldn) + slab4 + lane + 32 * c, o);
+      if (WRITE_ARG) stg_na(reinterpret_cast<int4*>(argmax + v * ldarg) + slab4 + lane + 32 * c, arg[c]);
+    }
+  }
+}
+
+template <int VEC, int kWideWarps>
+static int launch_fwd_wide(const float* P, int64_t ldp, const int32_t* indptr, const int32_t* indices, int32_t N,
+                           float* neigh, int64_t ldn, int32_t* argmax, int64_t ldarg, cudaStream_t st, int slabs = 1) {
+  int64_t grid = sm_count();
+  int64_t per_cta = ceil_div<int64_t>(N, grid);
+  per_cta = ceil_div<int64_t>(per_cta, kWideWarps) * kWideWarps;
+  grid = ceil_div<int64_t>(N, per_cta);
+  if (argmax)
+    segmax_fwd_wide_kernel<VEC, true, kWideWarps><<<dim3((unsigned)grid, slabs), kWideWarps * 32, 0, st>>>(P, ldp, indptr, indices, N, neigh, ldn, argmax, ldarg, per_cta);
+  else
+    segmax_fwd_wide_kernel<VEC, false, kWideWarps><<<dim3((unsigned)grid, slabs), kWideWarps * 32, 0, st>>>(P, ldp, indptr, indices, N, neigh, ldn, nullptr, 0, per_cta);
+  GTS_LAUNCH_CHECK();
+  return GTS_OK;
 }
 
 // Scalar fallback: any D / alignment.  One warp per node, lanes stride over columns.
@@ -244,11 +343,18 @@ static inline int seg_grid(int64_t warps_needed) {
 template <int LPN, int VEC>
 static int launch_fwd_vec(const float* P, int64_t ldp, const int32_t* indptr, const int32_t* indices, int32_t N,
                           int32_t D4, float* neigh, int64_t ldn, int32_t* argmax, int64_t ldarg, cudaStream_t st) {
-  const int64_t warps = ceil_div<int64_t>(N, 32 / LPN);
+  // one CTA per SM (768 threads for rows up to 2 chunks per lane, 512 above), each on a contiguous id range
+  constexpr int THREADS = VEC <= 2 ? 768 : (VEC <= 4 ? 384 : 256);
+  constexpr int NPW = 32 / LPN;
+  const int64_t per_pass = (int64_t)(THREADS / 32) * NPW;            // nodes one CTA touches per sweep
+  int64_t grid = sm_count();
+  int64_t per_cta = ceil_div<int64_t>(N, grid);
+  per_cta = ceil_div<int64_t>(per_cta, per_pass) * per_pass;         // whole sweeps
+  grid = ceil_div<int64_t>(N, per_cta);
   if (argmax)
-    segmax_fwd_vec_kernel<LPN, VEC, true><<<seg_grid(warps), kSegThreads, 0, st>>>(P, ldp, indptr, indices, N, D4, neigh, ldn, argmax, ldarg);
+    segmax_fwd_vec_kernel<LPN, VEC, true, THREADS><<<(int)grid, THREADS, 0, st>>>(P, ldp, indptr, indices, N, D4, neigh, ldn, argmax, ldarg, per_cta);
   else
-    segmax_fwd_vec_kernel<LPN, VEC, false><<<seg_grid(warps), kSegThreads, 0, st>>>(P, ldp, indptr, indices, N, D4, neigh, ldn, nullptr, 0);
+    segmax_fwd_vec_kernel<LPN, VEC, false, THREADS><<<(int)grid, THREADS, 0, st>>>(P, ldp, indptr, indices, N, D4, neigh, ldn, nullptr, 0, per_cta);
   GTS_LAUNCH_CHECK();
   return GTS_OK;
 }
@@ -271,6 +377,17 @@ int gts_segmax_fwd(const float* P, int64_t ldp, const int32_t* indptr, const int
   cudaStream_t st = as_stream(stream);
   const bool vec_ok = (D % 4 == 0) && (ldp % 4 == 0) && (ldn % 4 == 0) && (!argmax || ldarg % 4 == 0) &&
                       aligned16(P) && aligned16(neigh) && (!argmax || aligned16(argmax)) && D <= 1024;
+  static const bool no_wide = getenv("GTS_SEGMAX_GENERIC") != nullptr;   // A/B switch for profiling
+  static const int wide_warps = getenv("GTS_SEGMAX_WARPS") ? atoi(getenv("GTS_SEGMAX_WARPS")) : 32;
+  const bool wide_ok = !no_wide && vec_ok && (int64_t)n_nodes * (ldp / 4) < ((int64_t)1 << 31);
+  if (wide_ok && D == 128) return launch_fwd_wide<1, 32>(P, ldp, indptr, indices, n_nodes, neigh, ldn, argmax, ldarg, st);
+  if (wide_ok && D == 256) {
+    if (wide_warps == 48) return launch_fwd_wide<1, 24>(P, ldp, indptr, indices, n_nodes, neigh, ldn, argmax, ldarg, st, 2);
+    if (wide_warps == 64) return launch_fwd_wide<1, 32>(P, ldp, indptr, indices, n_nodes, neigh, ldn, argmax, ldarg, st, 2);
+    if (wide_warps == 24) return launch_fwd_wide<2, 24>(P, ldp, indptr, indices, n_nodes, neigh, ldn, argmax, ldarg, st);
+    if (wide_warps == 16) return launch_fwd_wide<2, 16>(P, ldp, indptr, indices, n_nodes, neigh, ldn, argmax, ldarg, st);
+    return launch_fwd_wide<2, 32>(P, ldp, indptr, indices, n_nodes, neigh, ldn, argmax, ldarg, st);
+  }
   if (vec_ok) {
     const int D4 = D / 4;
     if (D4 <= 4)   return launch_fwd_vec<4, 1>(P, ldp, indptr, indices, n_nodes, D4, neigh, ldn, argmax, ldarg, st);
