@@ -37,13 +37,15 @@ class GemmNtArgs(C.Structure):
         ("C", C.c_void_p), ("ldc", C.c_int64),
         ("M", C.c_int32), ("N", C.c_int32),
         ("act", C.c_int32), ("mode", C.c_int32),
+        ("bias2", C.c_void_p),
     ]
 
 
 class SageLayer(C.Structure):
     """struct gts_sage_layer (include/gts.h)."""
     _fields_ = [("din", C.c_int32), ("dout", C.c_int32), ("relu", C.c_int32), ("reserved", C.c_int32),
-                ("Wp", C.c_void_p), ("bp", C.c_void_p), ("Ws", C.c_void_p), ("Wn", C.c_void_p), ("b", C.c_void_p)]
+                ("Wp", C.c_void_p), ("bp", C.c_void_p), ("Ws", C.c_void_p), ("Wn", C.c_void_p), ("b", C.c_void_p),
+                ("b2", C.c_void_p)]
 
 
 class SageLayerGrads(C.Structure):

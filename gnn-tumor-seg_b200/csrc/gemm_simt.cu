@@ -54,7 +54,7 @@ template <int BM, int BN, int TM, int TN, bool A_KMAJOR, bool B_KMAJOR, bool SPL
 __global__ void __launch_bounds__(kSimtThreads)
 gemm_simt_kernel(Operand A1, Operand B1, int64_t K1, Operand A2, Operand B2, int64_t K2,
                  int64_t M, int64_t N, float* __restrict__ C, int64_t ldc,
-                 const float* __restrict__ bias, const float* __restrict__ aux, int64_t ldaux, int act,
+                 const float* __restrict__ bias, const float* __restrict__ bias2, const float* __restrict__ aux, int64_t ldaux, int act,
                  int64_t k_per_split, int64_t split_stride) {
   static_assert((BM / TM) * (BN / TN) == kSimtThreads, "thread tiling must cover the block tile");
   __shared__ float As[kBK][BM + 4];
@@ -114,6 +114,7 @@ gemm_simt_kernel(Operand A1, Operand B1, int64_t K1, Operand A2, Operand B2, int
       float v = acc[i][j];
       if (!SPLITK) {
         if (bias) v += bias[n];
+        if (bias2) v += bias2[n];
         if (act == GTS_ACT_RELU) v = fmaxf(v, 0.f);
         else if (act == GTS_ACT_MASK_POS) v = (aux[m * ldaux + n] > 0.f) ? v : 0.f;
       }
@@ -306,11 +307,11 @@ static int gemm_nt_simt(const gts_gemm_nt_args* a, cudaStream_t st) {
   if (a->N <= 16) {
     dim3 grid((unsigned)ceil_div<int64_t>(a->N, 16), (unsigned)ceil_div<int64_t>(a->M, 128));
     gemm_simt_kernel<128, 16, 8, 1, true, true, false><<<grid, kSimtThreads, 0, st>>>(
-        A1, B1, a->K1, A2, B2, K2, a->M, a->N, a->C, a->ldc, a->bias, a->aux, a->ldaux, a->act, 0, 0);
+        A1, B1, a->K1, A2, B2, K2, a->M, a->N, a->C, a->ldc, a->bias, a->bias2, a->aux, a->ldaux, a->act, 0, 0);
   } else {
     dim3 grid((unsigned)ceil_div<int64_t>(a->N, 128), (unsigned)ceil_div<int64_t>(a->M, 128));
     gemm_simt_kernel<128, 128, 8, 8, true, true, false><<<grid, kSimtThreads, 0, st>>>(
-        A1, B1, a->K1, A2, B2, K2, a->M, a->N, a->C, a->ldc, a->bias, a->aux, a->ldaux, a->act, 0, 0);
+        A1, B1, a->K1, A2, B2, K2, a->M, a->N, a->C, a->ldc, a->bias, a->bias2, a->aux, a->ldaux, a->act, 0, 0);
   }
   GTS_LAUNCH_CHECK();
   return GTS_OK;
@@ -335,10 +336,10 @@ static int gemm_tn_simt(const float* A, int64_t lda, const float* B, int64_t ldb
   dim3 grid(tiles_n, tiles_m, splits);
   if (small_m)
     gemm_simt_kernel<16, 128, 1, 8, false, false, true><<<grid, kSimtThreads, 0, st>>>(
-        Ao, Bo, K, none, none, 0, Mo, No, partial, No, nullptr, nullptr, 0, 0, kps, stride);
+        Ao, Bo, K, none, none, 0, Mo, No, partial, No, nullptr, nullptr, nullptr, 0, 0, kps, stride);
   else
     gemm_simt_kernel<128, 128, 8, 8, false, false, true><<<grid, kSimtThreads, 0, st>>>(
-        Ao, Bo, K, none, none, 0, Mo, No, partial, No, nullptr, nullptr, 0, 0, kps, stride);
+        Ao, Bo, K, none, none, 0, Mo, No, partial, No, nullptr, nullptr, nullptr, 0, 0, kps, stride);
   GTS_LAUNCH_CHECK();
   const int64_t total = stride;
   int blocks = (int)ceil_div<int64_t>(total, 256);

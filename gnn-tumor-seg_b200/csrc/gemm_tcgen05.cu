@@ -159,7 +159,7 @@ struct Params {
   float* C; int64_t ldc;
   // NT
   int kb1, kb2;           // k-blocks of source 1 / 2
-  const float* bias; const float* aux; int64_t ldaux; int act;
+  const float* bias; const float* bias2; const float* aux; int64_t ldaux; int act;
   // TN (split-K)
   int splits; int kb_per_split; int kb_total; int64_t split_stride;
 };
@@ -350,6 +350,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         const bool col_ok = col < p.N && c0 + cc < p.BN;
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!TN && p.bias && col_ok) b = *reinterpret_cast<const float4*>(p.bias + col);
+        if (!TN && p.bias2 && col_ok) {
+          const float4 b2 = *reinterpret_cast<const float4*>(p.bias2 + col);
+          b.x += b2.x; b.y += b2.y; b.z += b2.z; b.w += b2.w;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int rr = 4 * j + rsub;
@@ -490,6 +494,7 @@ bool gemm_nt_tcgen05_supported(const gts_gemm_nt_args* a) {
   if (two && (!tc::operand_ok(a->A2, a->lda2) || !tc::operand_ok(a->B2, a->ldb2))) return false;
   if (!tc::al16(a->C) || a->ldc % 4 != 0) return false;
   if (a->bias && !tc::al16(a->bias)) return false;
+  if (a->bias2 && !tc::al16(a->bias2)) return false;
   if (a->act == GTS_ACT_MASK_POS && (!tc::al16(a->aux) || a->ldaux % 4 != 0)) return false;
   return tc::get_encode() != nullptr;
 }
@@ -506,7 +511,7 @@ int gemm_nt_tcgen05(const gts_gemm_nt_args* a, cudaStream_t st) {
   p.M = a->M; p.N = a->N; p.C = a->C; p.ldc = a->ldc;
   p.kb1 = (a->K1 + BK - 1) / BK;
   p.kb2 = two ? (a->K2 + BK - 1) / BK : 0;
-  p.bias = a->bias; p.aux = a->aux; p.ldaux = a->ldaux; p.act = a->act;
+  p.bias = a->bias; p.bias2 = a->bias2; p.aux = a->aux; p.ldaux = a->ldaux; p.act = a->act;
   p.splits = 1;
   CUtensorMap tA1, tA2, tB1, tB2;
   if (!encode_2d(&tA1, a->A1, a->M, a->K1, a->lda1, BK, BM, rnd)) return GTS_ERR_CUDA;

@@ -76,8 +76,9 @@ static inline float* at(void* ws, size_t off) { return reinterpret_cast<float*>(
 
 static int nt(const float* A1, int64_t lda1, int K1, const float* B1, int64_t ldb1, const float* A2, int64_t lda2, int K2,
               const float* B2, int64_t ldb2, const float* bias, int act, const float* aux, int64_t ldaux, float* C,
-              int64_t ldc, int M, int N, int mode, gts_stream_t st) {
+              int64_t ldc, int M, int N, int mode, gts_stream_t st, const float* bias2 = nullptr) {
   gts_gemm_nt_args a;
+  a.bias2 = bias2;
   a.A1 = A1; a.lda1 = lda1; a.K1 = K1; a.A2 = A2; a.lda2 = lda2; a.K2 = K2;
   a.B1 = B1; a.ldb1 = ldb1; a.B2 = B2; a.ldb2 = ldb2; a.bias = bias; a.aux = aux; a.ldaux = ldaux;
   a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.act = act; a.mode = mode;
@@ -131,7 +132,7 @@ int gts_sage_forward(const gts_sage_layer* layers, int32_t n_layers,
     else if (training) { out = at(workspace, pl.out[l]); ldo = ly.dout; }
     else { out = at(workspace, (l & 1) ? pl.g1 : pl.g0); ldo = ly.dout; }
     GTS_TRY(nt(h, ldh, ly.din, ly.Ws, ly.din, neigh, ly.din, ly.din, ly.Wn, ly.din, ly.b,
-               ly.relu ? GTS_ACT_RELU : GTS_ACT_NONE, nullptr, 0, out, ldo, N, ly.dout, mode, stream));
+               ly.relu ? GTS_ACT_RELU : GTS_ACT_NONE, nullptr, 0, out, ldo, N, ly.dout, mode, stream, ly.b2));
     h = out; ldh = ldo;
   }
   return GTS_OK;

@@ -73,6 +73,13 @@ class DataParallelTrainer:
 
     ``loss_sums_fn(logits, labels, w) -> tensor[2] = [sum w*nll, sum w]``
     (differentiable in its first entry); default: the fused device kernel.
+
+    Gradient buffer: when the whole backward ran through gts_sage_backward, every
+    parameter gradient already is a view of ONE flat device buffer
+    (ops.last_flat_grads) with two spare floats at its end; the loss sums are
+    written there and the buffer is all-reduced in place — no per-parameter copy
+    or add kernels.  Any other network (GAT, the CPU oracle in the gloo tests)
+    goes through a packed copy of the gradients.
     """
 
     def __init__(self, net, class_weights, process_group=None, loss_sums_fn=None):
@@ -80,20 +87,61 @@ class DataParallelTrainer:
         self.class_weights = class_weights
         self.pg = process_group
         self.loss_sums_fn = loss_sums_fn or ce_sums_device
-        self.arena = GradArena(net.parameters())
+        self.params = [p for p in net.parameters() if p.requires_grad]
         self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.flat = None          # the buffer that was all-reduced in the last step
+        self.n_grad = 0
+
+    @property
+    def grads(self):
+        return self.flat[:self.n_grad]
+
+    @property
+    def extra(self):
+        return self.flat[self.n_grad:self.n_grad + 2]
+
+    def _flat_from_stack(self):
+        """The flat buffer of the last stack backward, if it backs every parameter gradient."""
+        if not self.class_weights.is_cuda:
+            return None
+        from . import ops
+        flat = ops.last_flat_grads["flat"]
+        if flat is None:
+            return None
+        base = flat.untyped_storage().data_ptr()
+        for p in self.params:
+            if p.grad is None or p.grad.untyped_storage().data_ptr() != base:
+                return None
+        return flat, ops.last_flat_grads["n_grad"]
 
     def forward_backward(self, graph, feats, labels):
         """Returns the GLOBAL weighted-mean loss (0-d tensor, no host sync);
         parameter .grad hold the global-batch gradients afterwards."""
-        self.arena.zero_()
+        for p in self.params:
+            p.grad = None                     # autograd then adopts the produced tensors: no accumulate kernels
+        if self.class_weights.is_cuda:
+            from . import ops
+            ops.last_flat_grads["flat"] = None
         logits = self.net(graph, feats)
         sums = self.loss_sums_fn(logits, labels, self.class_weights)
-        sums[0].backward()                      # un-normalised: d(sum w*nll)/dtheta accumulates into the arena
+        sums[0].backward()                      # un-normalised: d(sum w*nll)/dtheta
         with torch.no_grad():
-            self.arena.extra.copy_(sums.detach())
+            got = self._flat_from_stack()
+            if got is not None:
+                flat, n_grad = got
+            else:                               # generic path: pack, reduce, hand views back
+                n_grad = sum(p.numel() for p in self.params)
+                flat = torch.empty(n_grad + 2, dtype=torch.float32, device=self.params[0].device)
+                off = 0
+                for p in self.params:
+                    n = p.numel()
+                    flat[off:off + n].copy_(p.grad.reshape(-1))
+                    p.grad = flat[off:off + n].view_as(p)
+                    off += n
+            flat[n_grad:n_grad + 2].copy_(sums.detach())
             if self.world_size > 1:
-                dist.all_reduce(self.arena.flat, op=dist.ReduceOp.SUM, group=self.pg)
-            denom = self.arena.extra[1]
-            self.arena.grads.div_(denom)
-            return self.arena.extra[0] / denom
+                dist.all_reduce(flat[:n_grad + 2], op=dist.ReduceOp.SUM, group=self.pg)
+            denom = flat[n_grad + 1]
+            flat[:n_grad].div_(denom)
+            self.flat, self.n_grad = flat, n_grad
+            return flat[n_grad] / denom

@@ -169,7 +169,7 @@ class GraphSage(nn.Module):
         self.layers.append(SAGEConv(layer_sizes[-1], n_classes, aggregator_type, feat_drop=0, activation=None))
 
     def _stack_fast_path_ok(self):
-        return all(l._aggre_type == "pool" and l.norm is None and l._has_bias
+        return all(l._aggre_type == "pool" and l.norm is None
                    and (l.feat_drop.p == 0 or not self.training)
                    and (l.activation is None or l.activation is F.relu or l.activation is torch.relu)
                    for l in self.layers)
@@ -179,7 +179,8 @@ class GraphSage(nn.Module):
             # whole stack in one library call per direction (gts_sage_forward / gts_sage_backward)
             flat, relus = [], []
             for l in self.layers:
-                flat += [l.fc_pool.weight, l.fc_pool.bias, l.fc_self.weight, l.fc_neigh.weight, l._effective_bias()]
+                flat += [l.fc_pool.weight, l.fc_pool.bias, l.fc_self.weight, l.fc_self.bias, l.fc_neigh.weight,
+                         l.fc_neigh.bias]
                 relus.append(l.activation is not None)
             return ops.SageStackFn.apply(graph, features, tuple(relus), ops.deterministic_backward(), *flat)
         h = features

@@ -140,7 +140,7 @@ def edge_perm_compose(eid_csr, eid_csc):
 # ---------------------------------------------------------------------------
 # dense contractions
 # ---------------------------------------------------------------------------
-def gemm_nt(A1, B1, A2=None, B2=None, bias=None, act=ACT_NONE, aux=None, mode=None, out=None):
+def gemm_nt(A1, B1, A2=None, B2=None, bias=None, act=ACT_NONE, aux=None, mode=None, out=None, bias2=None):
     """act(A1 @ B1.T + A2 @ B2.T + bias); B* in nn.Linear layout [out,in]."""
     require_cuda(A1, B1, A2, B2, bias, aux)
     lib = _lib.load()
@@ -164,6 +164,10 @@ def gemm_nt(A1, B1, A2=None, B2=None, bias=None, act=ACT_NONE, aux=None, mode=No
         bias = _f32c(bias)
         assert bias.numel() == N
     a.bias = ptr(bias)
+    if bias2 is not None:
+        bias2 = _f32c(bias2)
+        assert bias2.numel() == N
+    a.bias2 = ptr(bias2)
     if aux is not None:
         aux = _row_major_2d(aux)
         assert tuple(aux.shape) == (M, N)
@@ -410,55 +414,76 @@ def sage_pool_layer(h, Wp, bp, Ws, Wn, b, graph, relu_out, input_is_relu=False, 
     return SagePoolLayerFn.apply(h, Wp, bp, Ws, Wn, b, graph, relu_out, input_is_relu, grad_premasked, deterministic)
 
 
+# the flat buffer behind the parameter gradients of the most recent SageStackFn.backward
+# (data-parallel trainer all-reduces it in place: no per-parameter copies)
+last_flat_grads = {"flat": None, "n_grad": 0}
+
+
 class SageStackFn(torch.autograd.Function):
     """GraphSage.forward over ALL SAGEConv('pool') layers as one libgts call, and the
     whole backward as another (gts_sage_forward / gts_sage_backward): no Python between
-    the ~20 kernels of a layer.  ``flat`` = (Wp, bp, Ws, Wn, b) per layer; ``relus`` =
-    per-layer ReLU flags."""
+    the ~20 kernels of a layer.  ``flat`` = (Wp, bp, Ws, bs, Wn, bn) per layer (bs / bn =
+    fc_self.bias / fc_neigh.bias, either may be None); ``relus`` = per-layer ReLU flags.
+    All parameter gradients are views of ONE flat buffer (``last_flat_grads``)."""
 
     @staticmethod
     def forward(ctx, graph, feats, relus, deterministic, *flat):
         require_cuda(feats, *flat)
         lib = _lib.load()
         L = len(relus)
-        assert len(flat) == 5 * L
+        assert len(flat) == 6 * L
         feats = _row_major_2d(feats)
         N = feats.shape[0]
         dev = feats.device
-        flat = tuple(_f32c(t) for t in flat)
+        flat = tuple(None if t is None else _f32c(t) for t in flat)
         layers = (_lib.SageLayer * L)()
         for l in range(L):
-            Wp, bp, Ws, Wn, b = flat[5 * l:5 * l + 5]
+            Wp, bp, Ws, bs, Wn, bn = flat[6 * l:6 * l + 6]
             layers[l].din, layers[l].dout, layers[l].relu = Ws.shape[1], Ws.shape[0], int(bool(relus[l]))
-            layers[l].Wp, layers[l].bp, layers[l].Ws, layers[l].Wn, layers[l].b = ptr(Wp), ptr(bp), ptr(Ws), ptr(Wn), ptr(b)
+            layers[l].Wp, layers[l].bp, layers[l].Ws, layers[l].Wn = ptr(Wp), ptr(bp), ptr(Ws), ptr(Wn)
+            layers[l].b, layers[l].b2 = ptr(bs), ptr(bn)
         training = any(ctx.needs_input_grad)
         mode = _gemm_mode
         ws = _workspace(lib.gts_sage_workspace_bytes(layers, L, N, int(training), mode), dev)
         indptr, indices = graph.csr
-        logits = torch.empty((N, flat[5 * (L - 1) + 2].shape[0]), dtype=torch.float32, device=dev)
+        logits = torch.empty((N, flat[6 * (L - 1) + 2].shape[0]), dtype=torch.float32, device=dev)
         check(lib.gts_sage_forward(layers, L, ptr(indptr), ptr(indices), N, ptr(feats), _ld(feats), ptr(logits),
                                    logits.shape[1], ptr(ws), ws.numel(), int(training), mode, stream_ptr()),
               "gts_sage_forward")
         _count(3 * L)
         if training:
-            ctx.save_for_backward(feats, ws, *flat)
+            ctx.save_for_backward(feats, ws, *[t for t in flat if t is not None])
+            ctx.present = [t is not None for t in flat]
             ctx.layers, ctx.graph, ctx.mode, ctx.deterministic = layers, graph, mode, deterministic
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
         lib = _lib.load()
-        feats, ws, *flat = ctx.saved_tensors
+        feats, ws, *saved = ctx.saved_tensors
+        it = iter(saved)
+        flat = [next(it) if pres else None for pres in ctx.present]
         layers, graph = ctx.layers, ctx.graph
         L = len(layers)
         N = feats.shape[0]
         dlogits = _row_major_2d(dlogits)
+        # one flat buffer: [dWp | dbp | dWs | dWn | db] per layer, then 2 spare floats (loss sums in DP)
+        sizes = []
+        for l in range(L):
+            Wp, bp, Ws, bs, Wn, bn = flat[6 * l:6 * l + 6]
+            sizes += [Wp.numel(), bp.numel(), Ws.numel(), Wn.numel(), Ws.shape[0]]
+        offs = [0]
+        for sz in sizes:
+            offs.append(offs[-1] + (sz + 3) // 4 * 4)             # keep every slice 16-byte aligned
+        flat_g = torch.zeros(offs[-1] + 4, dtype=torch.float32, device=feats.device)
         grads = (_lib.SageLayerGrads * L)()
         outs = []
         for l in range(L):
-            g5 = [torch.empty_like(t) for t in flat[5 * l:5 * l + 5]]
-            outs.extend(g5)
-            grads[l].dWp, grads[l].dbp, grads[l].dWs, grads[l].dWn, grads[l].db = (ptr(t) for t in g5)
+            Wp, bp, Ws, bs, Wn, bn = flat[6 * l:6 * l + 6]
+            v = [flat_g[offs[5 * l + k]:offs[5 * l + k] + sizes[5 * l + k]] for k in range(5)]
+            gWp, gbp, gWs, gWn, gb = v[0].view_as(Wp), v[1].view_as(bp), v[2].view_as(Ws), v[3].view_as(Wn), v[4]
+            grads[l].dWp, grads[l].dbp, grads[l].dWs, grads[l].dWn, grads[l].db = (ptr(t) for t in (gWp, gbp, gWs, gWn, gb))
+            outs += [gWp, gbp, gWs, gb if bs is not None else None, gWn, gb if bn is not None else None]
         dfeats = torch.empty_like(feats) if ctx.needs_input_grad[1] else None
         cptr = cidx = None
         if ctx.deterministic:
@@ -467,6 +492,7 @@ class SageStackFn(torch.autograd.Function):
                                     ptr(dlogits), _ld(dlogits), ptr(dfeats), (feats.shape[1] if dfeats is not None else 0),
                                     ptr(ws), ws.numel(), ctx.mode, stream_ptr()), "gts_sage_backward")
         _count(20 * L)
+        last_flat_grads["flat"], last_flat_grads["n_grad"] = flat_g, offs[-1]
         return (None, dfeats, None, None, *outs)
 
 

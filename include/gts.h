@@ -112,6 +112,7 @@ typedef struct gts_gemm_nt_args {
   int32_t M; int32_t N;
   int32_t act;   /* gts_act */
   int32_t mode;  /* gts_gemm_mode */
+  const float* bias2;   /* optional second bias vector, added to bias (DGL<=0.7 keeps fc_self.bias and fc_neigh.bias) */
 } gts_gemm_nt_args;
 
 GTS_API int gts_gemm_nt(const gts_gemm_nt_args* args, gts_stream_t stream);
@@ -180,11 +181,13 @@ GTS_API int gts_mask_pos(const float* grad, const float* ref, int64_t n, float* 
  * per-layer kernels are enqueued back to back without returning to Python.
  * Layer l: P = relu(h Wp^T + bp); neigh = segmax(P); out = act(h Ws^T + neigh Wn^T + b),
  * act = ReLU when relu != 0.  All pointers are device pointers; weights use
- * the nn.Linear layout [out,in]; b is the effective output bias.
+ * the nn.Linear layout [out,in]; the output bias is b + b2 (either may be NULL).
  * ------------------------------------------------------------------------ */
 typedef struct gts_sage_layer {
   int32_t din; int32_t dout; int32_t relu; int32_t reserved;
-  const float* Wp; const float* bp; const float* Ws; const float* Wn; const float* b;
+  const float* Wp; const float* bp; const float* Ws; const float* Wn;
+  const float* b;    /* output bias (fc_self.bias), nullable */
+  const float* b2;   /* second output bias (fc_neigh.bias), nullable; effective bias = b + b2 */
 } gts_sage_layer;
 
 typedef struct gts_sage_layer_grads {

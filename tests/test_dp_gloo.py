@@ -48,7 +48,7 @@ def _worker(rank, world, port, out_dir):
         csr, feats, labels = _make(mine)
         tr = dp.DataParallelTrainer(net, W, loss_sums_fn=_cpu_loss_sums)
         loss = tr.forward_backward(csr, feats, labels)
-        torch.save({"loss": loss, "grads": tr.arena.grads.clone(), "extra": tr.arena.extra.clone()},
+        torch.save({"loss": loss, "grads": tr.grads.clone(), "extra": tr.extra.clone()},
                    os.path.join(out_dir, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()
@@ -94,3 +94,17 @@ def test_world2_equals_single_process_union_batch(tmp_path):
     assert torch.allclose(r0["grads"], ref, atol=1e-6, rtol=1e-4)
     # naive averaging of per-rank mean losses would NOT match (data-dependent denominators)
     assert float(r0["extra"][1]) == pytest.approx(float(W[labels].sum()), rel=1e-6)
+
+
+def test_trainer_hands_back_views_of_the_reduced_buffer():
+    net = _net()
+    csr, feats, labels = _make([0, 1])
+    tr = dp.DataParallelTrainer(net, W, loss_sums_fn=_cpu_loss_sums)
+    loss = tr.forward_backward(csr, feats, labels)
+    ref = _net()
+    l2 = torch.nn.functional.cross_entropy(ref(csr, feats), labels, weight=W)
+    l2.backward()
+    assert abs(float(loss) - float(l2)) < 1e-5
+    for p, q in zip(net.parameters(), ref.parameters()):
+        assert torch.allclose(p.grad, q.grad, atol=1e-6, rtol=1e-4)
+        assert p.grad.untyped_storage().data_ptr() == tr.flat.untyped_storage().data_ptr()
