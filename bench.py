@@ -32,6 +32,8 @@ LAYER_SIZES = [256] * 7
 IN_FEATS, N_CLASSES = 20, 4
 CLASS_W = [0.1, 1.0, 2.0, 2.0]
 N_DISTINCT_GRAPHS = 8
+# BASELINE configs[2] / SURVEY §8 a5: GAT 4-head x256
+GAT_LAYER_SIZES, GAT_HEADS, GAT_RESIDUALS = [256] * 4, [4, 4, 4, 4], [False, False, True, False]
 
 
 def load_peaks():
@@ -234,7 +236,10 @@ def run_ours(args):
     n_edges = resident[0][0].number_of_edges()
 
     torch.manual_seed(0)
-    net = networks.GraphSage(IN_FEATS, LAYER_SIZES, N_CLASSES, "pool", 0).to(dev)
+    if args.model == "gat":
+        net = networks.GAT(IN_FEATS, GAT_LAYER_SIZES, N_CLASSES, GAT_HEADS, GAT_RESIDUALS).to(dev)
+    else:
+        net = networks.GraphSage(IN_FEATS, LAYER_SIZES, N_CLASSES, "pool", 0).to(dev)
     class_w = torch.tensor(CLASS_W, device=dev)
     trainer = dp.DataParallelTrainer(net, class_w)
 
@@ -298,6 +303,8 @@ def run_ours(args):
         return
 
     # ---- per-kernel breakdown and live roofline of the dominant + aggregation kernels ----
+    # rank 0 only from here on: no collectives (the other ranks are already waiting at the final barrier)
+    trainer.world_size = 1
     breakdown = kernel_breakdown(lambda: step(0), ops)
     D = 256
     Ps = [torch.relu(torch.randn(n_nodes, D, device=dev)) for _ in range(3)]      # 3 x 92 MB > L2
@@ -377,9 +384,12 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3"}[args.mode], "data": "synthetic",
         "edges_per_s": n_edges * world / (ms * 1e-3),
-        "config": {"workload": "GraphSAGE-pool 7x256 training fwd+CE+bwd, batch of 6 synthetic 15k-node supervoxel RAGs per GPU "
-                               "(BASELINE configs[1]; configs[3] for N>1: whole graphs per rank + one NCCL grad all-reduce)",
-                   "layer_sizes": LAYER_SIZES, "graphs_per_gpu": args.batch, "nodes_per_step_per_gpu": n_nodes,
+        "config": {"workload": ("GraphSAGE-pool 7x256 training fwd+CE+bwd, batch of 6 synthetic 15k-node supervoxel RAGs per GPU "
+                                "(BASELINE configs[1]; configs[3] for N>1: whole graphs per rank + one NCCL grad all-reduce)")
+                               if args.model == "sage" else
+                               ("GAT 4-head x256 (layer_sizes [256]*4, heads [4,4,4,4], residuals [F,F,T,F]) training fwd+CE+bwd, "
+                                "batch of 6 synthetic 15k-node supervoxel RAGs per GPU (BASELINE configs[2])"),
+                   "layer_sizes": LAYER_SIZES if args.model == "sage" else GAT_LAYER_SIZES, "graphs_per_gpu": args.batch, "nodes_per_step_per_gpu": n_nodes,
                    "edges_per_step_per_gpu": n_edges, "gemm_mode": args.mode,
                    "l2_policy": "inputs larger than L2: %d rotating device-resident batches, >2 GB of activations per step" % args.rotate,
                    "parallelism": "dp%d" % world},
@@ -407,6 +417,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default=os.environ.get("GTS_GEMM_MODE", "tf32x3"), choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--model", default="sage", choices=["sage", "gat"])
     ap.add_argument("--batch", type=int, default=6)
     ap.add_argument("--rotate", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
