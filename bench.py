@@ -187,12 +187,15 @@ def kernel_breakdown(step_fn, ops):
             return r
         return g
 
+    stack = ops.use_stack_path()
     try:
+        ops.set_stack_path(False)          # per-layer path: same kernels, visible to the wrappers
         for n in names:
             setattr(ops, n, wrap(n))
         step_fn()
         torch.cuda.synchronize()
     finally:
+        ops.set_stack_path(stack)
         for n in names:
             setattr(ops, n, orig[n])
     out = {}
