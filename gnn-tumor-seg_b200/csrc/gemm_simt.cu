@@ -10,7 +10,9 @@ namespace gts {
 
 int gemm_nt_tcgen05(const gts_gemm_nt_args* a, cudaStream_t st);   // gemm_tcgen05.cu
 int gemm_tn_tcgen05(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
-                    int32_t Mo, int32_t No, int64_t K, int32_t mode, void* ws, size_t ws_bytes, cudaStream_t st);
+                    int32_t Mo, int32_t No, int64_t K, int32_t mode, float* colsum_out, void* ws, size_t ws_bytes,
+                    cudaStream_t st);
+bool gemm_tn_tcgen05_fuses_colsum(int32_t mode);
 size_t gemm_tn_tcgen05_ws(int32_t Mo, int32_t No, int64_t K, int32_t mode);
 bool gemm_nt_tcgen05_supported(const gts_gemm_nt_args* a);
 bool gemm_tn_tcgen05_supported(const float* A, int64_t lda, const float* B, int64_t ldb, int32_t Mo, int32_t No, int64_t K);
@@ -396,8 +398,32 @@ int gts_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb,
   GTS_CHECK_ARG(A && B, "gts_gemm_tn: null operand");
   GTS_CHECK_ARG(mode >= GTS_GEMM_FP32 && mode <= GTS_GEMM_TF32X3, "gts_gemm_tn: unknown mode %d", mode);
   if (mode != GTS_GEMM_FP32 && gemm_tn_tcgen05_supported(A, lda, B, ldb, Mo, No, K))
-    return gemm_tn_tcgen05(A, lda, B, ldb, C, ldc, Mo, No, K, mode, workspace, workspace_bytes, st);
+    return gemm_tn_tcgen05(A, lda, B, ldb, C, ldc, Mo, No, K, mode, nullptr, workspace, workspace_bytes, st);
   return gemm_tn_simt(A, lda, B, ldb, C, ldc, Mo, No, K, workspace, workspace_bytes, st);
+}
+
+size_t gts_gemm_tn_colsum_workspace_bytes(int32_t Mo, int32_t No, int64_t K, int32_t mode) {
+  return gts_gemm_tn_workspace_bytes(Mo, No, K, mode) + gts_colsum_workspace_bytes(K, Mo);
+}
+
+int gts_gemm_tn_colsum(const float* A, int64_t lda, const float* B, int64_t ldb,
+                       float* C, int64_t ldc, int32_t Mo, int32_t No, int64_t K, int32_t mode,
+                       float* colsum_out, void* workspace, size_t workspace_bytes, gts_stream_t stream) {
+  GTS_CHECK_ARG(Mo >= 0 && No >= 0 && K >= 0, "gts_gemm_tn_colsum: negative size");
+  GTS_CHECK_ARG(colsum_out != nullptr || Mo == 0, "gts_gemm_tn_colsum: colsum_out is null");
+  GTS_CHECK_ARG(mode >= GTS_GEMM_FP32 && mode <= GTS_GEMM_TF32X3, "gts_gemm_tn_colsum: unknown mode %d", mode);
+  const size_t tn_bytes = gts_gemm_tn_workspace_bytes(Mo, No, K, mode);
+  const size_t need = tn_bytes + gts_colsum_workspace_bytes(K, Mo);
+  if (workspace_bytes < need || (need > 0 && workspace == nullptr)) {
+    set_error("gts_gemm_tn_colsum: workspace %zu < required %zu", workspace_bytes, need);
+    return GTS_ERR_WORKSPACE;
+  }
+  if (Mo > 0 && No > 0 && K > 0 && C && A && B && gemm_tn_tcgen05_fuses_colsum(mode) &&
+      gemm_tn_tcgen05_supported(A, lda, B, ldb, Mo, No, K))
+    return gemm_tn_tcgen05(A, lda, B, ldb, C, ldc, Mo, No, K, mode, colsum_out, workspace, tn_bytes, as_stream(stream));
+  int rc = gts_gemm_tn(A, lda, B, ldb, C, ldc, Mo, No, K, mode, workspace, tn_bytes, stream);
+  if (rc != GTS_OK) return rc;
+  return gts_colsum(A, lda, K, Mo, colsum_out, reinterpret_cast<char*>(workspace) + tn_bytes, workspace_bytes - tn_bytes, stream);
 }
 
 size_t gts_colsum_workspace_bytes(int64_t rows, int32_t cols) {

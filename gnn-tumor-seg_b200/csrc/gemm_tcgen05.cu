@@ -162,6 +162,7 @@ struct Params {
   const float* bias; const float* bias2; const float* aux; int64_t ldaux; int act;
   // TN (split-K)
   int splits; int kb_per_split; int kb_total; int64_t split_stride;
+  float* colsum_partial;   // TN, A-in-TMEM kernel: [splits][M] column sums of the A operand (or null)
 };
 
 // ---------------------------------------------------------------------------
@@ -179,6 +180,79 @@ struct Params {
 __device__ __forceinline__ float tf32_lo(float x) {
   const float lo = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
   return __uint_as_float(__float_as_uint(lo) + 0x1000u);
+}
+
+// Epilogue of one accumulator tile for one warp: the warp owns TMEM lanes [q*32, q*32+32) (rows m0..m0+31 of C)
+// and the 32-column chunks c_first, c_first + c_step, ...  TMEM -> registers -> padded smem tile -> coalesced
+// 128-bit global stores with the fused bias / ReLU / ReLU-mask.
+template <bool TN>
+__device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t t_base, int m0, int n0, float* Cout, float* stg,
+                                              int lane, int c_first, int c_step, bool masked, uint64_t* full_bar,
+                                              uint32_t full_phase) {
+  const int cc = (lane & 7) * 4;
+  const int rsub = lane >> 3;
+  // ReLU-mask source: fetched one chunk ahead so its latency hides behind the TMEM load
+  float4 aux_cur[8], aux_nxt[8];
+  auto load_aux = [&](int c0, float4 (&dst)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t row = (int64_t)m0 + 4 * j + rsub;
+      const int col = n0 + c0 + cc;
+      dst[j] = (row < p.M && col < p.N && c0 + cc < p.BN)
+                   ? ldg_nc_na(reinterpret_cast<const float4*>(p.aux + row * p.ldaux + col))
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+    if (masked && c_first < p.BN) load_aux(c_first, aux_cur);
+
+  mbar_wait(full_bar, full_phase);
+  tcgen05_fence_after();
+  for (int c0 = c_first; c0 < p.BN; c0 += c_step) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(t_base + c0, v);
+    if (masked && c0 + c_step < p.BN) load_aux(c0 + c_step, aux_nxt);
+    tmem_ld_wait();
+    // lane = row: park the 32 columns of this row in the padded staging tile
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * j) =
+          make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                      __uint_as_float(v[4 * j + 3]));
+    __syncwarp();
+    // coalesced write-out: 8 lanes cover one 128-byte row segment, 4 rows per instruction
+    const int col = n0 + c0 + cc;
+    const bool col_ok = col < p.N && c0 + cc < p.BN;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!TN && p.bias && col_ok) b = *reinterpret_cast<const float4*>(p.bias + col);
+    if (!TN && p.bias2 && col_ok) {
+      const float4 b2 = *reinterpret_cast<const float4*>(p.bias2 + col);
+      b.x += b2.x; b.y += b2.y; b.z += b2.z; b.w += b2.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int rr = 4 * j + rsub;
+      const int64_t row = (int64_t)m0 + rr;
+      if (row < p.M && col_ok) {
+        float4 x = *reinterpret_cast<const float4*>(stg + rr * EPI_LD + cc);
+        if (!TN) {
+          x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+          if (p.act == GTS_ACT_RELU) {
+            x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+          } else if (masked) {
+            const float4 a = aux_cur[j];
+            x.x = a.x > 0.f ? x.x : 0.f; x.y = a.y > 0.f ? x.y : 0.f;
+            x.z = a.z > 0.f ? x.z : 0.f; x.w = a.w > 0.f ? x.w : 0.f;
+          }
+        }
+        *reinterpret_cast<float4*>(Cout + row * p.ldc + col) = x;
+      }
+    }
+    __syncwarp();
+    if (masked) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) aux_cur[j] = aux_nxt[j];
+    }
+  }
 }
 
 template <bool TN, bool X3>
@@ -307,8 +381,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     const int n_col_groups = L::EPI_WARPS / 4;     // warps sharing a lane quarter split the column chunks
     const int col_group = ew >> 2;
     float* stg = epi_stage + ew * 32 * EPI_LD;
-    const int cc = (lane & 7) * 4;
-    const int rsub = lane >> 3;
     const bool masked = !TN && p.act == GTS_ACT_MASK_POS;
     int it = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
@@ -321,69 +393,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       float* Cout = p.C + (TN ? (int64_t)split * p.split_stride : 0);
       const uint32_t t_base = tmem_base + (uint32_t)acc * MAX_BN + ((uint32_t)(q * 32) << 16);
 
-      // ReLU-mask source: fetched one chunk ahead so its latency hides behind the TMEM load
-      float4 aux_cur[8], aux_nxt[8];
-      auto load_aux = [&](int c0, float4 (&dst)[8]) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int64_t row = (int64_t)m0 + 4 * j + rsub;
-          const int col = n0 + c0 + cc;
-          dst[j] = (row < p.M && col < p.N && c0 + cc < p.BN)
-                       ? ldg_nc_na(reinterpret_cast<const float4*>(p.aux + row * p.ldaux + col))
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      };
-      const int c_first = col_group * 32, c_step = n_col_groups * 32;
-      if (masked && c_first < p.BN) load_aux(c_first, aux_cur);
-
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tcgen05_fence_after();
-      for (int c0 = c_first; c0 < p.BN; c0 += c_step) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_base + c0, v);
-        if (masked && c0 + c_step < p.BN) load_aux(c0 + c_step, aux_nxt);
-        tmem_ld_wait();
-        // lane = row: park the 32 columns of this row in the padded staging tile
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * j) =
-              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                          __uint_as_float(v[4 * j + 3]));
-        __syncwarp();
-        // coalesced write-out: 8 lanes cover one 128-byte row segment, 4 rows per instruction
-        const int col = n0 + c0 + cc;
-        const bool col_ok = col < p.N && c0 + cc < p.BN;
-        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!TN && p.bias && col_ok) b = *reinterpret_cast<const float4*>(p.bias + col);
-        if (!TN && p.bias2 && col_ok) {
-          const float4 b2 = *reinterpret_cast<const float4*>(p.bias2 + col);
-          b.x += b2.x; b.y += b2.y; b.z += b2.z; b.w += b2.w;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int rr = 4 * j + rsub;
-          const int64_t row = (int64_t)m0 + rr;
-          if (row < p.M && col_ok) {
-            float4 x = *reinterpret_cast<const float4*>(stg + rr * EPI_LD + cc);
-            if (!TN) {
-              x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
-              if (p.act == GTS_ACT_RELU) {
-                x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
-              } else if (masked) {
-                const float4 a = aux_cur[j];
-                x.x = a.x > 0.f ? x.x : 0.f; x.y = a.y > 0.f ? x.y : 0.f;
-                x.z = a.z > 0.f ? x.z : 0.f; x.w = a.w > 0.f ? x.w : 0.f;
-              }
-            }
-            *reinterpret_cast<float4*>(Cout + row * p.ldc + col) = x;
-          }
-        }
-        __syncwarp();
-        if (masked) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) aux_cur[j] = aux_nxt[j];
-        }
-      }
+      epilogue_tile<TN>(p, t_base, m0, n0, Cout, stg, lane, col_group * 32, n_col_groups * 32, masked,
+                        &tmem_full[acc], acc_phase);
       tcgen05_fence_before();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
@@ -408,6 +419,302 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         mbar_arrive(&split_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+
+// ---------------------------------------------------------------------------
+// 3xTF32 with the A operand in TENSOR MEMORY (tcgen05.mma ... [d], [a_tmem], b_desc).
+//
+// Why: in the all-shared-memory 3xTF32 scheme above every k-block moves 288 KB
+// through shared memory (TMA 48 + split 96 + three MMA passes reading A and B,
+// 144) against 1536 tensor-pipe cycles -> the 128 B/clk shared-memory port caps
+// the tensor pipe at ~68 % (ncu: ~50 % achieved).  Here four warps read the
+// landed A tile ONCE, split it in registers and park hi | lo in TMEM
+// (tcgen05.st, lane = A row, column = k), so the MMA only streams B from shared
+// memory: 224 KB per k-block.
+//
+// Warp roles (576 threads): 0 = TMA producer, 1 = MMA issuer + TMEM allocator,
+// 2..5 = A split -> TMEM (warp % 4 = TMEM lane quarter), 6..9 = B split in shared
+// memory, 10..17 = epilogue (two warps per lane quarter).
+// TMEM: columns [0,256) one fp32 accumulator, [256 + 64 s, +64) A hi | lo of stage s.
+// TN form: A = [nodes, Mo] row-major (MN-major box), so the split thread of feature
+// m walks its column of the landed box — and sums it on the way: the bias
+// gradient (column sum of the A operand) is a by-product of the weight-gradient GEMM.
+// ---------------------------------------------------------------------------
+// BNC = widest N tile (UMMA N) of the variant:
+//   256: 2 stages of (A 16 | B 32 | B lo 32 KB), ONE 256-column accumulator (epilogue exposed), 8 epilogue warps;
+//   128: 4 stages of (A 16 | B 16 | B lo 16 KB), TWO 128-column accumulators (epilogue overlaps the next
+//        tile), 4 epilogue warps.  A 256-wide output is two N tiles, i.e. A is fetched twice (the second time
+//        from L2) — but twice the bytes are in flight per SM, and with only ~48 KB per stage the 2-stage form
+//        is bound by the L2 -> SM round trip (measured: 3000+ clk per k-block against 1536 of tensor work).
+template <int BNC>
+struct TsCfg {
+  static constexpr int STAGES = BNC == 256 ? 2 : 4;
+  static constexpr int ACC_BUFS = BNC == 256 ? 1 : 2;
+  static constexpr int EPI_WARPS = BNC == 256 ? 8 : 4;
+  static constexpr int B_BYTES = BNC * BK * 4;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + 2 * B_BYTES;     // A | B hi | B lo
+  static constexpr int THREADS = (10 + EPI_WARPS) * 32;
+  static constexpr int epi_off = STAGES * STAGE_BYTES;
+  static constexpr int epi_bytes = EPI_WARPS * 32 * EPI_LD * 4;
+  static constexpr int bar_off = epi_off + epi_bytes;
+  // full[S], empty[S], a_ready[S], b_ready[S], tmem_full[ACC_BUFS], tmem_empty[ACC_BUFS], tmem_ptr
+  static constexpr int total = bar_off + (4 * STAGES + 2 * ACC_BUFS) * 8 + 16;
+  static constexpr int dyn_bytes = total + 1024;
+  static_assert(dyn_bytes <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
+  static constexpr uint32_t A_COL0 = 256;       // first TMEM column of the A ring (64 columns per stage: hi | lo)
+  static_assert(A_COL0 + 64 * STAGES <= TMEM_COLS && ACC_BUFS * BNC <= (int)A_COL0, "TMEM column budget");
+};
+
+__device__ __forceinline__ void tcgen05_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                    uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D = f32, A = B = tf32; A always K-major (it lives in TMEM), B K-major (NT) or MN-major (TN).
+__host__ __device__ constexpr uint32_t make_idesc_ts(int m, int n, bool b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+
+template <bool TN, int BNC>
+__global__ void __launch_bounds__(TsCfg<BNC>::THREADS, 1)
+gemm_x3ts_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                 const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, const Params p) {
+  using L = TsCfg<BNC>;
+  constexpr int STAGES = L::STAGES;
+  constexpr int STAGE_BYTES = L::STAGE_BYTES;
+  constexpr int ACC_BUFS = L::ACC_BUFS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::bar_off);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* a_ready = full_bar + 2 * STAGES;
+  uint64_t* b_ready = full_bar + 3 * STAGES;
+  uint64_t* tmem_full = full_bar + 4 * STAGES;
+  uint64_t* tmem_empty = tmem_full + ACC_BUFS;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + ACC_BUFS);
+  float* epi_stage = reinterpret_cast<float*>(smem + L::epi_off);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+      mbar_init(&a_ready[s], 128);
+      mbar_init(&b_ready[s], 128);
+    }
+    for (int a = 0; a < ACC_BUFS; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], L::EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&tmA1); prefetch_tmap(&tmB1);
+    if (!TN && p.kb2 > 0) { prefetch_tmap(&tmA2); prefetch_tmap(&tmB2); }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n_work = TN ? p.tiles_m * p.tiles_n * p.splits : p.tiles_m * p.tiles_n;
+  const uint32_t stage_tx_bytes = (uint32_t)(BM + p.BN) * BK * 4;
+
+  // k-block range of work item w
+  auto k_range = [&](int w, int& kb_beg, int& kb_end) {
+    kb_beg = 0; kb_end = p.kb1 + p.kb2;
+    if (TN) { const int split = w % p.splits; kb_beg = split * p.kb_per_split; kb_end = min(p.kb_total, kb_beg + p.kb_per_split); }
+  };
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int tile = TN ? w / p.splits : w;
+        const int m0 = (tile / p.tiles_n) * BM;
+        const int n0 = (tile % p.tiles_n) * p.BN;
+        int kb_beg, kb_end;
+        k_range(w, kb_beg, kb_end);
+        for (int kb = kb_beg; kb < kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], stage_tx_bytes);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          if (!TN) {
+            const bool second = kb >= p.kb1;
+            const int k0 = (second ? kb - p.kb1 : kb) * BK;
+            tma_load_2d(sa, second ? &tmA2 : &tmA1, &full_bar[stage], k0, m0);
+            tma_load_2d(sb, second ? &tmB2 : &tmB1, &full_bar[stage], k0, n0);
+          } else {
+            const int k0 = kb * BK;    // node rows
+#pragma unroll
+            for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * 4096, &tmA1, &full_bar[stage], m0 + 32 * c, k0);
+            for (int c = 0; c < p.BN / 32; ++c) tma_load_2d(sb + c * 4096, &tmB1, &full_bar[stage], n0 + 32 * c, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_ts(BM, p.BN, TN);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+        int kb_beg, kb_end;
+        k_range(w, kb_beg, kb_end);
+        const int acc = it % ACC_BUFS;
+        const uint32_t acc_phase = (uint32_t)(it / ACC_BUFS) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);          // the epilogue has drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BNC;
+        for (int kb = kb_beg; kb < kb_end; ++kb) {
+          mbar_wait(&a_ready[stage], phase);
+          mbar_wait(&b_ready[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sb = smem_u32(smem + stage * STAGE_BYTES) + A_STAGE_BYTES;
+          const uint32_t a_hi = tmem_base + L::A_COL0 + (uint32_t)stage * 64;
+          const uint32_t a_lo = a_hi + 32;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint32_t koff = TN ? k * 1024 : k * UMMA_K * 4;
+            const uint32_t lbo = TN ? 4096 : 16, sbo = TN ? 512 : 1024;
+            const uint32_t lay = TN ? kLayoutSw128Base32 : kLayoutSw128;
+            const uint64_t db = make_smem_desc(sb + koff, lbo, sbo, lay);
+            const uint64_t db_lo = make_smem_desc(sb + L::B_BYTES + koff, lbo, sbo, lay);
+            const uint32_t first = (kb > kb_beg || k > 0) ? 1u : 0u;
+            tcgen05_mma_tf32_ts(d_tmem, a_lo + k * UMMA_K, db, idesc, first);   // lo * hi
+            tcgen05_mma_tf32_ts(d_tmem, a_hi + k * UMMA_K, db_lo, idesc, 1u);   // hi * lo
+            tcgen05_mma_tf32_ts(d_tmem, a_hi + k * UMMA_K, db, idesc, 1u);      // hi * hi
+          }
+          tcgen05_commit(&empty_bar[stage]);       // smem slot and TMEM A slot reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tcgen05_commit(&tmem_full[acc]);           // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp < 6) {
+    // ======================= A split -> TMEM =======================
+    const int q = warp & 3;                        // TMEM lane quarter of this warp
+    const int r = q * 32 + lane;                   // row of the 128-row A tile (NT) / feature column (TN)
+    int stage = 0; uint32_t phase = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      int kb_beg, kb_end;
+      k_range(w, kb_beg, kb_end);
+      float csum = 0.f;
+      for (int kb = kb_beg; kb < kb_end; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        const uint8_t* sa = smem + stage * STAGE_BYTES;
+        uint32_t hi[32], lo[32];
+        if (!TN) {
+          // K-major tile, 128B swizzle: row r at r * 128, 16-byte chunk c stored at chunk c ^ (r & 7)
+          const uint8_t* row = sa + r * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 x = *reinterpret_cast<const float4*>(row + ((c ^ (r & 7)) << 4));
+            hi[4 * c + 0] = __float_as_uint(x.x); hi[4 * c + 1] = __float_as_uint(x.y);
+            hi[4 * c + 2] = __float_as_uint(x.z); hi[4 * c + 3] = __float_as_uint(x.w);
+          }
+        } else {
+          // MN-major boxes [32 node rows][32 features], SWIZZLE_128B_ATOM_32B: box q holds this warp's 32
+          // features; node row k at k * 128, 32-byte unit u stored at unit u ^ (k & 3)
+          const uint8_t* box = sa + q * 4096 + (lane & 7) * 4;
+          const int u = lane >> 3;
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float x = *reinterpret_cast<const float*>(box + k * 128 + ((u ^ (k & 3)) << 5));
+            hi[k] = __float_as_uint(x);
+            csum += x;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) lo[i] = __float_as_uint(tf32_lo(__uint_as_float(hi[i])));
+        const uint32_t t_a = tmem_base + ((uint32_t)(q * 32) << 16) + L::A_COL0 + (uint32_t)stage * 64;
+        tmem_st_32x32b_x32(t_a, hi);
+        tmem_st_32x32b_x32(t_a + 32, lo);
+        tmem_st_wait();
+        tcgen05_fence_before();
+        mbar_arrive(&a_ready[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (TN && p.colsum_partial) {
+        const int split = w % p.splits, tile = w / p.splits;
+        const int m = (tile / p.tiles_n) * BM + r;
+        if (tile % p.tiles_n == 0 && m < p.M) p.colsum_partial[(int64_t)split * p.M + m] = csum;
+      }
+    }
+  } else if (warp < 10) {
+    // ======================= B split in shared memory =======================
+    const int t = threadIdx.x - 6 * 32;            // 0..127
+    const int n_vec = p.BN * BK * 4 / 16;          // float4 count of the used part of B
+    int stage = 0; uint32_t phase = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      int kb_beg, kb_end;
+      k_range(w, kb_beg, kb_end);
+      for (int kb = kb_beg; kb < kb_end; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        const float4* hi = reinterpret_cast<const float4*>(smem + stage * STAGE_BYTES + A_STAGE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES + A_STAGE_BYTES + L::B_BYTES);
+#pragma unroll 4
+        for (int i = t; i < n_vec; i += 128) {
+          const float4 x = hi[i];
+          lo[i] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+        mbar_arrive(&b_ready[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ======================= epilogue warps =======================
+    const int ew = warp - 10;
+    const int q = warp & 3;
+    const int col_group = ew >> 2;
+    float* stg = epi_stage + ew * 32 * EPI_LD;
+    const bool masked = !TN && p.act == GTS_ACT_MASK_POS;
+    int it = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+      int tile = w, split = 0;
+      if (TN) { split = w % p.splits; tile = w / p.splits; }
+      const int m0 = (tile / p.tiles_n) * BM + q * 32;
+      const int n0 = (tile % p.tiles_n) * p.BN;
+      float* Cout = p.C + (TN ? (int64_t)split * p.split_stride : 0);
+      const int acc = it % ACC_BUFS;
+      const uint32_t t_base = tmem_base + (uint32_t)acc * BNC + ((uint32_t)(q * 32) << 16);
+      epilogue_tile<TN>(p, t_base, m0, n0, Cout, stg, lane, col_group * 32, (L::EPI_WARPS / 4) * 32, masked,
+                        &tmem_full[acc], (uint32_t)(it / ACC_BUFS) & 1);
+      tcgen05_fence_before();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
   }
 
@@ -485,8 +792,36 @@ static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMa
   return GTS_OK;
 }
 
-static int pick_bn(int n, int granule) {
-  int bn = n >= MAX_BN ? MAX_BN : ((n + granule - 1) / granule) * granule;
+template <bool TN, int BNC>
+static int launch_ts(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1, const CUtensorMap& b2,
+                     const Params& p, int n_work, cudaStream_t st) {
+  using L = TsCfg<BNC>;
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_x3ts_kernel<TN, BNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::dyn_bytes);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d) failed: %s", L::dyn_bytes, cudaGetErrorString(e)); return GTS_ERR_CUDA; }
+    done = true;
+  }
+  const int grid = n_work < sm_count() ? n_work : sm_count();
+  gemm_x3ts_kernel<TN, BNC><<<grid, L::THREADS, L::dyn_bytes, st>>>(a1, a2, b1, b2, p);
+  GTS_LAUNCH_CHECK();
+  return GTS_OK;
+}
+
+// widest N tile of the A-in-TMEM kernel: 128 (default: 4 stages, overlapped epilogue) or 256 (GTS_X3_BN=256)
+static int ts_bn_cap() {
+  static const int cap = (getenv("GTS_X3_BN") && atoi(getenv("GTS_X3_BN")) == 256) ? 256 : 128;
+  return cap;
+}
+
+// A/B switch for profiling: GTS_X3_SMEM=1 keeps the all-shared-memory 3xTF32 kernel.
+static bool x3_in_tmem() {
+  static const bool legacy = getenv("GTS_X3_SMEM") != nullptr;
+  return !legacy;
+}
+
+static int pick_bn(int n, int granule, int cap = MAX_BN) {
+  int bn = n >= cap ? cap : ((n + granule - 1) / granule) * granule;
   return bn;
 }
 
@@ -509,8 +844,9 @@ int gemm_nt_tcgen05(const gts_gemm_nt_args* a, cudaStream_t st) {
   const bool x3 = a->mode == GTS_GEMM_TF32X3;
   const bool rnd = !x3;      // 1xTF32: TMA rounds to nearest; 3xTF32: raw fp32 (the MMA truncates, lo = x - trunc(x))
   const bool two = a->A2 && a->B2 && a->K2 > 0;
+  const bool in_tmem = x3 && x3_in_tmem();
   Params p{};
-  p.BN = pick_bn(a->N, 16);
+  p.BN = pick_bn(a->N, 16, in_tmem ? ts_bn_cap() : MAX_BN);
   p.tiles_m = (a->M + BM - 1) / BM;
   p.tiles_n = (a->N + p.BN - 1) / p.BN;
   p.M = a->M; p.N = a->N; p.C = a->C; p.ldc = a->ldc;
@@ -528,6 +864,9 @@ int gemm_nt_tcgen05(const gts_gemm_nt_args* a, cudaStream_t st) {
     tA2 = tA1; tB2 = tB1;
   }
   const int n_work = p.tiles_m * p.tiles_n;
+  if (in_tmem)
+    return ts_bn_cap() == 256 ? launch_ts<false, 256>(tA1, tA2, tB1, tB2, p, n_work, st)
+                              : launch_ts<false, 128>(tA1, tA2, tB1, tB2, p, n_work, st);
   return x3 ? launch<false, true>(tA1, tA2, tB1, tB2, p, n_work, st)
             : launch<false, false>(tA1, tA2, tB1, tB2, p, n_work, st);
 }
@@ -538,9 +877,9 @@ bool gemm_tn_tcgen05_supported(const float* A, int64_t lda, const float* B, int6
   return tc::get_encode() != nullptr;
 }
 
-static void tn_plan(int32_t Mo, int32_t No, int64_t K, tc::Params& p) {
+static void tn_plan(int32_t Mo, int32_t No, int64_t K, int32_t mode, tc::Params& p) {
   using namespace tc;
-  p.BN = pick_bn(No, 32);
+  p.BN = pick_bn(No, 32, (mode == GTS_GEMM_TF32X3 && x3_in_tmem()) ? ts_bn_cap() : MAX_BN);
   p.tiles_m = (Mo + BM - 1) / BM;
   p.tiles_n = (No + p.BN - 1) / p.BN;
   p.kb_total = (int)((K + BK - 1) / BK);
@@ -553,32 +892,48 @@ static void tn_plan(int32_t Mo, int32_t No, int64_t K, tc::Params& p) {
   p.split_stride = (int64_t)Mo * No;
 }
 
+// workspace: [splits][Mo][No] partial products, then [splits][Mo] partial column sums of A
 size_t gemm_tn_tcgen05_ws(int32_t Mo, int32_t No, int64_t K, int32_t mode) {
-  (void)mode;
   if (Mo < 1 || No < 1 || K < 1) return 0;
   tc::Params p{};
-  tn_plan(Mo, No, K, p);
-  return align_up((size_t)p.splits * (size_t)Mo * (size_t)No * sizeof(float), 256);
+  tn_plan(Mo, No, K, mode, p);
+  return align_up((size_t)p.splits * (size_t)Mo * (size_t)No * sizeof(float), 256) +
+         align_up((size_t)p.splits * (size_t)Mo * sizeof(float), 256);
 }
 
+// true when gemm_tn_tcgen05 can produce the column sums of A as a by-product (3xTF32, A staged through TMEM)
+bool gemm_tn_tcgen05_fuses_colsum(int32_t mode) { return mode == GTS_GEMM_TF32X3 && tc::x3_in_tmem(); }
+
 int gemm_tn_tcgen05(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
-                    int32_t Mo, int32_t No, int64_t K, int32_t mode, void* ws, size_t ws_bytes, cudaStream_t st) {
+                    int32_t Mo, int32_t No, int64_t K, int32_t mode, float* colsum_out, void* ws, size_t ws_bytes,
+                    cudaStream_t st) {
   using namespace tc;
   const bool x3 = mode == GTS_GEMM_TF32X3;
   Params p{};
-  tn_plan(Mo, No, K, p);
-  const size_t need = align_up((size_t)p.splits * (size_t)Mo * (size_t)No * sizeof(float), 256);
+  tn_plan(Mo, No, K, mode, p);
+  const size_t prod_bytes = align_up((size_t)p.splits * (size_t)Mo * (size_t)No * sizeof(float), 256);
+  const size_t need = prod_bytes + align_up((size_t)p.splits * (size_t)Mo * sizeof(float), 256);
   if (!ws || ws_bytes < need) { set_error("gts_gemm_tn: workspace %zu < required %zu", ws_bytes, need); return GTS_ERR_WORKSPACE; }
   p.M = Mo; p.N = No;
   p.C = reinterpret_cast<float*>(ws); p.ldc = No;
+  const bool in_tmem = x3 && x3_in_tmem();
+  if (colsum_out && !in_tmem) { set_error("gts_gemm_tn: fused column sums need the 3xTF32 A-in-TMEM kernel"); return GTS_ERR_INVALID; }
+  float* cs_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + prod_bytes);
+  p.colsum_partial = colsum_out ? cs_partial : nullptr;
   CUtensorMap tA, tB;
   if (!encode_2d(&tA, A, K, Mo, lda, 32, BK, !x3, true)) return GTS_ERR_CUDA;
   if (!encode_2d(&tB, B, K, No, ldb, 32, BK, !x3, true)) return GTS_ERR_CUDA;
   const int n_work = p.tiles_m * p.tiles_n * p.splits;
-  int rc = x3 ? launch<true, true>(tA, tA, tB, tB, p, n_work, st) : launch<true, false>(tA, tA, tB, tB, p, n_work, st);
+  int rc = in_tmem ? (ts_bn_cap() == 256 ? launch_ts<true, 256>(tA, tA, tB, tB, p, n_work, st)
+                                         : launch_ts<true, 128>(tA, tA, tB, tB, p, n_work, st))
+                   : (x3 ? launch<true, true>(tA, tA, tB, tB, p, n_work, st) : launch<true, false>(tA, tA, tB, tB, p, n_work, st));
   if (rc != GTS_OK) return rc;
   launch_splitk_reduce(p.C, p.split_stride, p.splits, Mo, No, C, ldc, st);
   GTS_LAUNCH_CHECK();
+  if (colsum_out) {
+    launch_splitk_reduce(cs_partial, Mo, p.splits, 1, Mo, colsum_out, Mo, st);
+    GTS_LAUNCH_CHECK();
+  }
   return GTS_OK;
 }
 

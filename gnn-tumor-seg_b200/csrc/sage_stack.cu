@@ -47,8 +47,8 @@ static bool make_plan(const gts_sage_layer* layers, int L, int64_t N, bool train
     pl.wt1 = take(max_w * 4);
     size_t gw = 256, cw = 256;
     for (int l = 0; l < L; ++l) {
-      size_t a = gts_gemm_tn_workspace_bytes(layers[l].dout, layers[l].din, N, mode);
-      size_t b = gts_gemm_tn_workspace_bytes(layers[l].din, layers[l].din, N, mode);
+      size_t a = gts_gemm_tn_colsum_workspace_bytes(layers[l].dout, layers[l].din, N, mode);
+      size_t b = gts_gemm_tn_colsum_workspace_bytes(layers[l].din, layers[l].din, N, mode);
       gw = a > gw ? a : gw; gw = b > gw ? b : gw;
       size_t c = gts_colsum_workspace_bytes(N, layers[l].dout), d = gts_colsum_workspace_bytes(N, layers[l].din);
       cw = c > cw ? c : cw; cw = d > cw ? d : cw;
@@ -165,10 +165,9 @@ int gts_sage_backward(const gts_sage_layer* layers, const gts_sage_layer_grads* 
     const float* neigh = at(workspace, pl.neigh[l]);
     const int32_t* arg = reinterpret_cast<const int32_t*>(at(workspace, pl.arg[l]));
     void* gws = at(workspace, pl.gemm_ws);
-    void* cws = at(workspace, pl.colsum_ws);
     // (dZ already carries this layer's ReLU mask: the consumer's epilogue applied (out > 0))
-    GTS_TRY(gts_colsum(dZ, ldz, N, ly.dout, g.db, cws, pl.colsum_ws_bytes, stream));
-    GTS_TRY(gts_gemm_tn(dZ, ldz, h, ldh, g.dWs, ly.din, ly.dout, ly.din, N, mode, gws, pl.gemm_ws_bytes, stream));
+    // dWs = dZ^T h and db = column sums of dZ (one pass over dZ in the 3xTF32 mode)
+    GTS_TRY(gts_gemm_tn_colsum(dZ, ldz, h, ldh, g.dWs, ly.din, ly.dout, ly.din, N, mode, g.db, gws, pl.gemm_ws_bytes, stream));
     GTS_TRY(gts_gemm_tn(dZ, ldz, neigh, ly.din, g.dWn, ly.din, ly.dout, ly.din, N, mode, gws, pl.gemm_ws_bytes, stream));
     // dNeigh' = (dZ Wn) * (neigh > 0)
     float* WnT = at(workspace, pl.wt0);
@@ -181,8 +180,7 @@ int gts_sage_backward(const gts_sage_layer* layers, const gts_sage_layer_grads* 
       GTS_TRY(gts_segmax_bwd_det(dNeigh, ly.din, arg, ly.din, csc_indptr, csc_indices, N, ly.din, dP, ly.din, stream));
     else
       GTS_TRY(gts_segmax_bwd(dNeigh, ly.din, arg, ly.din, N, ly.din, dP, ly.din, N, stream));
-    GTS_TRY(gts_gemm_tn(dP, ly.din, h, ldh, g.dWp, ly.din, ly.din, ly.din, N, mode, gws, pl.gemm_ws_bytes, stream));
-    GTS_TRY(gts_colsum(dP, ly.din, N, ly.din, g.dbp, cws, pl.colsum_ws_bytes, stream));
+    GTS_TRY(gts_gemm_tn_colsum(dP, ly.din, h, ldh, g.dWp, ly.din, ly.din, ly.din, N, mode, g.dbp, gws, pl.gemm_ws_bytes, stream));
     if (l > 0 || dfeats) {
       float* WsT = at(workspace, pl.wt0);
       float* WpT = at(workspace, pl.wt1);

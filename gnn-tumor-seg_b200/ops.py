@@ -202,6 +202,27 @@ def gemm_tn(A, B, mode=None):
     return out
 
 
+def gemm_tn_colsum(A, B, mode=None):
+    """(A.T @ B, A.sum(0)) — a weight gradient and the bias gradient sharing its A operand.
+    In the tf32x3 mode the column sums are a by-product of the kernel that stages A through
+    tensor memory; otherwise gts_gemm_tn + gts_colsum behind the same entry point."""
+    require_cuda(A, B)
+    lib = _lib.load()
+    A = _row_major_2d(A)
+    B = _row_major_2d(B)
+    K, Mo = A.shape
+    No = B.shape[1]
+    assert B.shape[0] == K
+    m = _gemm_mode if mode is None else (GEMM_MODES[mode] if isinstance(mode, str) else mode)
+    out = torch.empty((Mo, No), dtype=torch.float32, device=A.device)
+    cs = torch.empty(Mo, dtype=torch.float32, device=A.device)
+    ws = _workspace(lib.gts_gemm_tn_colsum_workspace_bytes(Mo, No, K, m), A.device)
+    check(lib.gts_gemm_tn_colsum(ptr(A), _ld(A), ptr(B), _ld(B), ptr(out), No, Mo, No, K, m, ptr(cs), ptr(ws),
+                                 ws.numel(), stream_ptr()), "gts_gemm_tn_colsum")
+    _count(3)
+    return out, cs
+
+
 def colsum(A):
     require_cuda(A)
     lib = _lib.load()
@@ -391,8 +412,7 @@ class SagePoolLayerFn(torch.autograd.Function):
         relu_out, input_is_relu, grad_premasked, deterministic = ctx.flags
         dOut = _row_major_2d(dOut)
         dZ = mask_pos(dOut, out) if (relu_out and not grad_premasked) else dOut
-        db = colsum(dZ)
-        dWs = gemm_tn(dZ, h)
+        dWs, db = gemm_tn_colsum(dZ, h)
         dWn = gemm_tn(dZ, neigh)
         # dNeigh' = (dZ Wn) * (neigh > 0): ReLU mask of fc_pool folded here, since
         # neigh[v,k] = P[arg[v,k],k] (Appendix A.1)
@@ -400,8 +420,7 @@ class SagePoolLayerFn(torch.autograd.Function):
         csc = ctx.graph.csc[:2] if deterministic else None
         dP = segmax_bwd(dNeigh, arg, h.shape[0], csc=csc)
         del dNeigh
-        dWp = gemm_tn(dP, h)
-        dbp = colsum(dP)
+        dWp, dbp = gemm_tn_colsum(dP, h)
         dh = None
         if ctx.needs_input_grad[0]:
             dh = gemm_nt(dZ, transpose(Ws), dP, transpose(Wp),

@@ -124,6 +124,16 @@ GTS_API int gts_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb
                 float* C, int64_t ldc, int32_t Mo, int32_t No, int64_t K, int32_t mode,
                 void* workspace, size_t workspace_bytes, gts_stream_t stream);
 
+/* Weight gradient plus the bias gradient that shares its A operand:
+ * C = A^T B and colsum_out[m] = sum_k A[k,m].  In GTS_GEMM_TF32X3 the column sums are a by-product of the
+ * kernel that stages A through tensor memory (no extra pass over A); otherwise gts_gemm_tn + gts_colsum.
+ * Replaces the autograd of nn.Linear (weight.grad and bias.grad) inside DGL SAGEConv
+ * (reference model/networks.py:35). */
+GTS_API size_t gts_gemm_tn_colsum_workspace_bytes(int32_t Mo, int32_t No, int64_t K, int32_t mode);
+GTS_API int gts_gemm_tn_colsum(const float* A, int64_t lda, const float* B, int64_t ldb,
+                       float* C, int64_t ldc, int32_t Mo, int32_t No, int64_t K, int32_t mode,
+                       float* colsum_out, void* workspace, size_t workspace_bytes, gts_stream_t stream);
+
 /* out[c] = sum_r A[r,c]  (bias gradients).  Deterministic two-pass. */
 GTS_API size_t gts_colsum_workspace_bytes(int64_t rows, int32_t cols);
 GTS_API int gts_colsum(const float* A, int64_t lda, int64_t rows, int32_t cols, float* out,

@@ -50,6 +50,28 @@ def test_gemm_tn(cuda_dev, mode, K, Mo, No):
     assert _rel(out.cpu(), ref) < TOL[mode]
 
 
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3", "tf32"])
+@pytest.mark.parametrize("K,Mo,No", [(90000, 256, 256), (1234, 4, 256), (777, 256, 20), (33, 20, 20), (40001, 128, 64)])
+def test_gemm_tn_colsum(cuda_dev, mode, K, Mo, No):
+    """Weight gradient + bias gradient from one entry point (fused in the tf32x3 mode: the column
+    sums come out of the warps that stage A through tensor memory)."""
+    g = torch.Generator().manual_seed(K + 7 * Mo)
+    A = torch.randn(K, Mo, generator=g); B = torch.randn(K, No, generator=g)
+    out, cs = ops.gemm_tn_colsum(A.to(cuda_dev), B.to(cuda_dev), mode=mode)
+    assert _rel(out.cpu(), A.double().T @ B.double()) < TOL[mode]
+    assert _rel(cs.cpu(), A.double().sum(0)) < 1e-5          # column sums are plain fp32 adds in every mode
+
+
+def test_gemm_tn_colsum_integer_exact(cuda_dev):
+    """Integer-valued operands: products and sums are exact in every arithmetic mode -> bit-exact."""
+    g = torch.Generator().manual_seed(3)
+    A = torch.randint(-3, 4, (5000, 256), generator=g).float(); B = torch.randint(-3, 4, (5000, 256), generator=g).float()
+    for mode in ("fp32", "tf32x3", "tf32"):
+        out, cs = ops.gemm_tn_colsum(A.to(cuda_dev), B.to(cuda_dev), mode=mode)
+        assert torch.equal(out.cpu(), A.T @ B)
+        assert torch.equal(cs.cpu(), A.sum(0))
+
+
 def test_gemm_strided_operands(cuda_dev):
     big = torch.randn(300, 512)
     A = big[:, 128:384]                       # ld 512
