@@ -92,6 +92,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 22)) __trap();    // watchdog: a protocol bug must fault, not hang the GPU
   }
 }
+// non-blocking probe: the MMA issuer's barriers are almost always complete already, and every clock it spends
+// not issuing is exposed once the (shallow) tensor-core issue queue has drained
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -102,16 +113,35 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap) {
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tcgen05_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                                 uint32_t accumulate) {
+// Whole-warp forms (one elected lane issues).  The MMA warp runs its loop with all 32 lanes and warp-uniform
+// operands: operands that the compiler can prove uniform stay in uniform registers, whereas operands of a
+// single-lane branch cost an ELECT / R2UR.BROADCAST loop of ~11 instructions around every UTCHMMA — and the
+// issuing thread is effectively synchronous with the tensor pipe, so that overhead is not hidden (measured:
+// 98 -> 66 clk per 64-clk MMA).
+__device__ __forceinline__ void tcgen05_commit_elect(uint32_t bar_addr) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_tf32_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_tf32_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -272,7 +302,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* epi_stage = reinterpret_cast<float*>(smem + L::epi_off);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);    // provably warp-uniform
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -330,9 +360,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer =======================
-    if (lane == 0) {
+    // ======================= MMA issuer (whole warp, one elected lane issues) =======================
+    {
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = make_idesc(BM, p.BN, TN);
+      const uint32_t smem0 = smem_u32(smem);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
@@ -340,13 +372,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         const uint32_t acc_phase = (it >> 1) & 1;
         int kb_beg = 0, kb_end = p.kb1 + p.kb2;
         if (TN) { const int split = w % p.splits; kb_beg = split * p.kb_per_split; kb_end = min(p.kb_total, kb_beg + p.kb_per_split); }
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        if (!mbar_test(&tmem_empty[acc], acc_phase ^ 1)) mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * MAX_BN;
+        const uint32_t d_tmem = tmem_u + (uint32_t)acc * MAX_BN;
         for (int kb = kb_beg; kb < kb_end; ++kb) {
-          mbar_wait(X3 ? &split_bar[stage] : &full_bar[stage], phase);
+          uint64_t* rb = X3 ? &split_bar[stage] : &full_bar[stage];
+          if (!mbar_test(rb, phase)) mbar_wait(rb, phase);
           tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sa = smem0 + stage * STAGE_BYTES;
           const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -361,17 +394,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             if (X3) {
               const uint64_t da_lo = make_smem_desc(sa + OPER_BYTES + koff, lbo, sbo, lay);
               const uint64_t db_lo = make_smem_desc(sb + OPER_BYTES + koff, lbo, sbo, lay);
-              tcgen05_mma_tf32(d_tmem, da_lo, db, idesc, first);   // lo * hi
-              tcgen05_mma_tf32(d_tmem, da, db_lo, idesc, 1u);      // hi * lo
-              tcgen05_mma_tf32(d_tmem, da, db, idesc, 1u);         // hi * hi
+              tcgen05_mma_tf32_elect(d_tmem, da_lo, db, idesc, first);   // lo * hi
+              tcgen05_mma_tf32_elect(d_tmem, da, db_lo, idesc, 1u);      // hi * lo
+              tcgen05_mma_tf32_elect(d_tmem, da, db, idesc, 1u);         // hi * hi
             } else {
-              tcgen05_mma_tf32(d_tmem, da, db, idesc, first);
+              tcgen05_mma_tf32_elect(d_tmem, da, db, idesc, first);
             }
           }
-          tcgen05_commit(&empty_bar[stage]);       // smem slot reusable once these MMAs retire
+          tcgen05_commit_elect(smem_u32(&empty_bar[stage]));       // smem slot reusable once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit(&tmem_full[acc]);           // accumulator complete -> epilogue
+        tcgen05_commit_elect(smem_u32(&tmem_full[acc]));           // accumulator complete -> epilogue
       }
     }
   } else if (warp < 2 + L::EPI_WARPS) {
@@ -475,14 +508,6 @@ struct TsCfg {
   static_assert(A_COL0 + 64 * STAGES <= TMEM_COLS && ACC_BUFS * BNC <= (int)A_COL0, "TMEM column budget");
 };
 
-__device__ __forceinline__ void tcgen05_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                                    uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -521,7 +546,7 @@ gemm_x3ts_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + ACC_BUFS);
   float* epi_stage = reinterpret_cast<float*>(smem + L::epi_off);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);    // provably warp-uniform
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -585,9 +610,11 @@ gemm_x3ts_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer =======================
-    if (lane == 0) {
+    // ======================= MMA issuer (whole warp, one elected lane issues) =======================
+    {
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = make_idesc_ts(BM, p.BN, TN);
+      const uint32_t smem0 = smem_u32(smem);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
@@ -595,15 +622,15 @@ gemm_x3ts_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         k_range(w, kb_beg, kb_end);
         const int acc = it % ACC_BUFS;
         const uint32_t acc_phase = (uint32_t)(it / ACC_BUFS) & 1;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);          // the epilogue has drained this accumulator
+        if (!mbar_test(&tmem_empty[acc], acc_phase ^ 1)) mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // the epilogue has drained this accumulator
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BNC;
+        const uint32_t d_tmem = tmem_u + (uint32_t)acc * BNC;
         for (int kb = kb_beg; kb < kb_end; ++kb) {
-          mbar_wait(&a_ready[stage], phase);
-          mbar_wait(&b_ready[stage], phase);
+          if (!mbar_test(&a_ready[stage], phase)) mbar_wait(&a_ready[stage], phase);
+          if (!mbar_test(&b_ready[stage], phase)) mbar_wait(&b_ready[stage], phase);
           tcgen05_fence_after();
-          const uint32_t sb = smem_u32(smem + stage * STAGE_BYTES) + A_STAGE_BYTES;
-          const uint32_t a_hi = tmem_base + L::A_COL0 + (uint32_t)stage * 64;
+          const uint32_t sb = smem0 + stage * STAGE_BYTES + A_STAGE_BYTES;
+          const uint32_t a_hi = tmem_u + L::A_COL0 + (uint32_t)stage * 64;
           const uint32_t a_lo = a_hi + 32;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -613,14 +640,14 @@ gemm_x3ts_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
             const uint64_t db = make_smem_desc(sb + koff, lbo, sbo, lay);
             const uint64_t db_lo = make_smem_desc(sb + L::B_BYTES + koff, lbo, sbo, lay);
             const uint32_t first = (kb > kb_beg || k > 0) ? 1u : 0u;
-            tcgen05_mma_tf32_ts(d_tmem, a_lo + k * UMMA_K, db, idesc, first);   // lo * hi
-            tcgen05_mma_tf32_ts(d_tmem, a_hi + k * UMMA_K, db_lo, idesc, 1u);   // hi * lo
-            tcgen05_mma_tf32_ts(d_tmem, a_hi + k * UMMA_K, db, idesc, 1u);      // hi * hi
+            tcgen05_mma_tf32_ts_elect(d_tmem, a_lo + k * UMMA_K, db, idesc, first);   // lo * hi
+            tcgen05_mma_tf32_ts_elect(d_tmem, a_hi + k * UMMA_K, db_lo, idesc, 1u);   // hi * lo
+            tcgen05_mma_tf32_ts_elect(d_tmem, a_hi + k * UMMA_K, db, idesc, 1u);      // hi * hi
           }
-          tcgen05_commit(&empty_bar[stage]);       // smem slot and TMEM A slot reusable once these MMAs retire
+          tcgen05_commit_elect(smem_u32(&empty_bar[stage]));       // smem slot and TMEM A slot reusable once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit(&tmem_full[acc]);           // accumulator complete -> epilogue
+        tcgen05_commit_elect(smem_u32(&tmem_full[acc]));           // accumulator complete -> epilogue
       }
     }
   } else if (warp < 6) {
@@ -727,6 +754,380 @@ gemm_x3ts_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------
+// CTA-pair form of the A-in-TMEM 3xTF32 kernel (tcgen05.mma.cta_group::2, M = 256, N <= 128 per tile).
+//
+// What the measurements of the one-CTA forms said (profiles/r01_gemm_x3_pipeline.md):
+//  * the tensor pipe does 128 clk per 128x256x8 tf32 MMA (1.07 PFLOP/s chip-wide) — the kernels ran at half of it;
+//  * per-hop clock64 traces: one ring slot takes ~5500 clk from "seen empty" to "seen empty again" (TMA ~1100,
+//    split + hand-over ~2000, MMA 1536, commit ~300) — more than the 2-3 slots that fit beside the lo copies can
+//    hide, and most of the hand-over was a cluster-scope release fence on the arrive, not work;
+//  * an epilogue that is NOT overlapped costs 26 us per 92 MB output: all SMs store at once and the burst runs at
+//    the ~3.5 TB/s HBM write rate with nothing else in flight.
+// Hence: a CTA pair shares B (each CTA lands, splits and feeds half of the N rows: TMA bytes, split work and
+// operand reads per flop halve), N tiles of 128 so that TWO accumulators (2 x 128 TMEM columns) fit beside a
+// 4-slot A ring (4 x 64 columns) and the epilogue of tile i overlaps the main loop of tile i+1, and 32 KB
+// stages so that SIX of them are in flight.  A 256-wide output is two N tiles (A comes from L2 the second time).
+//
+// Both CTAs run the same warp roles on their own 128 rows of A / C; the MMA is issued by the leader (cluster
+// rank 0) only, its a_ready / b_ready / tmem_empty barriers collect (plain, CTA-scope-release) remote arrivals
+// from both CTAs, and tcgen05.commit multicasts "stage free" / "A slot free" / "accumulator full" to both.
+// ---------------------------------------------------------------------------
+struct Ts2Cfg {
+  static constexpr int BN_MAX = 128;                                   // UMMA N of a pair tile
+  static constexpr int KSUB = 1;                                       // k-blocks (of 32) per ring slot: one barrier round per 24 MMAs
+  static constexpr int STAGES = 6;                                     // shared-memory ring
+  static constexpr int A_SLOTS = 4;                                    // TMEM ring of split A tiles
+  static constexpr int ACC_BUFS = 2;
+  static constexpr int EPI_WARPS = 4;
+  static constexpr int B_HALF_BYTES = (BN_MAX / 2) * BK * 4;           // 8 KB: this CTA's half of the N rows
+  static constexpr int SUB_BYTES = A_STAGE_BYTES + 2 * B_HALF_BYTES;   // one k-block: A | B half hi | B half lo = 32 KB
+  static constexpr int STAGE_BYTES = KSUB * SUB_BYTES;
+  static constexpr int THREADS = (10 + EPI_WARPS) * 32;
+  static constexpr int epi_off = STAGES * STAGE_BYTES;
+  static constexpr int epi_bytes = EPI_WARPS * 32 * EPI_LD * 4;
+  static constexpr int bar_off = epi_off + epi_bytes;
+  // full[S], empty[S], ready[A], a_free[A], tmem_full[2], tmem_empty[2], tmem_ptr
+  static constexpr int total = bar_off + (2 * STAGES + 2 * A_SLOTS + 2 * ACC_BUFS) * 8 + 16;
+  static constexpr int dyn_bytes = total + 1024;
+  static_assert(dyn_bytes <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
+  static constexpr uint32_t A_COL0 = ACC_BUFS * BN_MAX;                // 256
+  static_assert(A_COL0 + 64 * KSUB * A_SLOTS <= TMEM_COLS, "TMEM column budget");
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+// remote arrive with the default (release, CTA scope) semantics: a cluster-scope release here costs ~1400 clk
+// per hand-over (measured); what crosses the CTAs is ordered by the tcgen05 / proxy fences, not by this arrive
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// whole-warp call, one elected lane commits
+__device__ __forceinline__ void tcgen05_commit_mc2_elect(uint32_t bar_addr) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(bar_addr), "h"((uint16_t)3) : "memory");
+}
+
+
+// The twelve MMAs of one 32-wide k-block of the 3xTF32 scheme (4 k-steps x {lo*hi, hi*lo, hi*hi}) as ONE asm
+// block: the issuing thread is effectively synchronous with the tensor pipe (measured: every scalar
+// instruction between two tcgen05.mma adds to the issue time), so all descriptors and TMEM addresses are
+// formed before the first MMA and the twelve instructions go out back to back.  Called by the WHOLE MMA warp with
+// warp-uniform operands (one elected lane issues): operands that the compiler can prove uniform live in uniform
+// registers; per-thread operands cost an ELECT / R2UR.BROADCAST loop of ~11 instructions around every UTCHMMA.
+// b_lo32 / l_lo32: low words of the B hi / B lo descriptors of k-step 0, k16: descriptor step per k-step (16-byte units).
+__device__ __forceinline__ void mma_x3_block_ts2(uint32_t d_tmem, uint32_t a_hi, uint32_t b_lo32, uint32_t l_lo32,
+                                                 uint32_t desc_hi32, uint32_t k16, uint32_t idesc, uint32_t first) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pf, pt, pe;\n\t"
+      ".reg .b32 x1, x2, x3, y1, y2, y3, ah1, ah2, ah3, al0, al1, al2, al3;\n\t"
+      ".reg .b64 b0, b1, b2, b3, l0, l1, l2, l3;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pf, %7, 0;\n\t"
+      "setp.eq.b32 pt, %7, %7;\n\t"
+      "add.u32 x1, %2, %5;\n\t add.u32 x2, x1, %5;\n\t add.u32 x3, x2, %5;\n\t"
+      "add.u32 y1, %3, %5;\n\t add.u32 y2, y1, %5;\n\t add.u32 y3, y2, %5;\n\t"
+      "mov.b64 b0, {%2, %4};\n\t mov.b64 b1, {x1, %4};\n\t mov.b64 b2, {x2, %4};\n\t mov.b64 b3, {x3, %4};\n\t"
+      "mov.b64 l0, {%3, %4};\n\t mov.b64 l1, {y1, %4};\n\t mov.b64 l2, {y2, %4};\n\t mov.b64 l3, {y3, %4};\n\t"
+      "add.u32 ah1, %1, 8;\n\t add.u32 ah2, %1, 16;\n\t add.u32 ah3, %1, 24;\n\t"
+      "add.u32 al0, %1, 32;\n\t add.u32 al1, %1, 40;\n\t add.u32 al2, %1, 48;\n\t add.u32 al3, %1, 56;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [al0], b0, %6, pf;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], l0, %6, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], b0, %6, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [al1], b1, %6, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [ah1], l1, %6, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [ah1], b1, %6, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [al2], b2, %6, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [ah2], l2, %6, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [ah2], b2, %6, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [al3], b3, %6, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [ah3], l3, %6, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [ah3], b3, %6, pt;\n\t"
+      "}"
+      ::"r"(d_tmem), "r"(a_hi), "r"(b_lo32), "r"(l_lo32), "r"(desc_hi32), "r"(k16), "r"(idesc), "r"(first) : "memory");
+}
+
+template <bool TN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Ts2Cfg::THREADS, 1)
+gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                  const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, const Params p) {
+  using L = Ts2Cfg;
+  constexpr int STAGES = L::STAGES;
+  constexpr int A_SLOTS = L::A_SLOTS;
+  constexpr int ACC_BUFS = L::ACC_BUFS;
+  constexpr int STAGE_BYTES = L::STAGE_BYTES;
+  constexpr int KSUB = L::KSUB;
+  constexpr int SUB_BYTES = L::SUB_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  // the same offset in both CTAs (the dynamic window starts at the same shared::cta address in every CTA of a kernel)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::bar_off);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* ready = full_bar + 2 * STAGES;           // A split in TMEM and B lo in shared memory, both CTAs (leader's copy is used)
+  uint64_t* a_free = ready + A_SLOTS;
+  uint64_t* tmem_full = a_free + A_SLOTS;
+  uint64_t* tmem_empty = tmem_full + ACC_BUFS;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + ACC_BUFS);
+  float* epi_stage = reinterpret_cast<float*>(smem + L::epi_off);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);    // provably warp-uniform
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();           // 0 = leader (issues the MMAs), 1 = peer
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+  const int half_bn = p.BN >> 1;                     // N rows of B this CTA lands and feeds
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);                   // multicast commit of the leader
+    }
+    for (int s = 0; s < A_SLOTS; ++s) {
+      mbar_init(&ready[s], 16);                      // (4 A-split + 4 B-split warps) x 2 CTAs
+      mbar_init(&a_free[s], 1);                      // multicast commit of the leader
+    }
+    for (int a = 0; a < ACC_BUFS; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 2 * L::EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&tmA1); prefetch_tmap(&tmB1);
+    if (!TN && p.kb2 > 0) { prefetch_tmap(&tmA2); prefetch_tmap(&tmB2); }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();                                // barriers initialised and TMEM allocated in BOTH CTAs
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // work item w -> (pair tile of 256 rows, N tile, split);  tiles_m counts 256-row pair tiles
+  const int n_work = TN ? p.tiles_m * p.tiles_n * p.splits : p.tiles_m * p.tiles_n;
+  const uint32_t stage_tx_bytes = (uint32_t)(BM + half_bn) * BK * 4;
+
+  auto k_range = [&](int w, int& kb_beg, int& kb_end) {
+    kb_beg = 0; kb_end = p.kb1 + p.kb2;
+    if (TN) { const int split = w % p.splits; kb_beg = split * p.kb_per_split; kb_end = min(p.kb_total, kb_beg + p.kb_per_split); }
+  };
+
+  if (warp == 0) {
+    // ======================= TMA producer (each CTA: its 128 rows of A, its half of B) =======================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = cluster_id; w < n_work; w += n_clusters) {
+        const int tile = TN ? w / p.splits : w;
+        const int m0 = (tile / p.tiles_n) * (2 * BM) + (int)rank * BM;
+        const int n0 = (tile % p.tiles_n) * p.BN + (int)rank * half_bn;
+        int kb_beg, kb_end;
+        k_range(w, kb_beg, kb_end);
+        for (int kb = kb_beg; kb < kb_end; kb += KSUB) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const int nsub = min(KSUB, kb_end - kb);
+          mbar_arrive_expect_tx(&full_bar[stage], stage_tx_bytes * (uint32_t)nsub);
+          for (int j = 0; j < nsub; ++j) {
+            uint8_t* sa = smem + stage * STAGE_BYTES + j * SUB_BYTES;
+            uint8_t* sb = sa + A_STAGE_BYTES;
+            const int kj = kb + j;
+            if (!TN) {
+              const bool second = kj >= p.kb1;
+              const int k0 = (second ? kj - p.kb1 : kj) * BK;
+              tma_load_2d(sa, second ? &tmA2 : &tmA1, &full_bar[stage], k0, m0);
+              tma_load_2d(sb, second ? &tmB2 : &tmB1, &full_bar[stage], k0, n0);
+            } else {
+              const int k0 = kj * BK;    // node rows
+#pragma unroll
+              for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * 4096, &tmA1, &full_bar[stage], m0 + 32 * c, k0);
+              for (int c = 0; c < half_bn / 32; ++c) tma_load_2d(sb + c * 4096, &tmB1, &full_bar[stage], n0 + 32 * c, k0);
+            }
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer (leader CTA only; the whole warp runs the loop, one elected lane issues) =======================
+    if (rank == 0) {
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);          // warp-uniform copy
+      const uint32_t idesc = make_idesc_ts(2 * BM, p.BN, TN);
+      // descriptor of a B tile at shared-memory address 0; the address field (bits 0..13, 16-byte units) is added per use
+      const uint64_t desc0 = make_smem_desc(0, TN ? 4096 : 16, TN ? 512 : 1024, TN ? kLayoutSw128Base32 : kLayoutSw128);
+      const uint32_t desc0_lo = (uint32_t)desc0, desc0_hi = (uint32_t)(desc0 >> 32);
+      const uint32_t koff16 = (TN ? 1024 : UMMA_K * 4) >> 4;
+      const uint32_t sb0 = (smem_u32(smem) + A_STAGE_BYTES) >> 4;
+      const uint32_t empty0 = smem_u32(&empty_bar[0]), afree0 = smem_u32(&a_free[0]), tfull0 = smem_u32(&tmem_full[0]);
+      int stage = 0;
+      int slot = 0; uint32_t sphase = 0;
+      int it = 0;
+      for (int w = cluster_id; w < n_work; w += n_clusters, ++it) {
+        int kb_beg, kb_end;
+        k_range(w, kb_beg, kb_end);
+        const int acc = it % ACC_BUFS;
+        const uint32_t acc_phase = (uint32_t)(it / ACC_BUFS) & 1;
+        if (!mbar_test(&tmem_empty[acc], acc_phase ^ 1)) mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // drained by both CTAs' epilogues
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_u + (uint32_t)acc * L::BN_MAX;
+        for (int kb = kb_beg; kb < kb_end; kb += KSUB) {
+          if (!mbar_test(&ready[slot], sphase)) mbar_wait(&ready[slot], sphase);
+          tcgen05_fence_after();
+          const int nsub = min(KSUB, kb_end - kb);
+          for (int j = 0; j < nsub; ++j) {
+            const uint32_t b_lo32 = desc0_lo + sb0 + (uint32_t)(stage * STAGE_BYTES + j * SUB_BYTES) / 16;
+            const uint32_t a_hi = tmem_u + L::A_COL0 + (uint32_t)(slot * KSUB + j) * 64;
+            mma_x3_block_ts2(d_tmem, a_hi, b_lo32, b_lo32 + (L::B_HALF_BYTES >> 4), desc0_hi, koff16, idesc,
+                             (kb > kb_beg || j > 0) ? 1u : 0u);
+          }
+          tcgen05_commit_mc2_elect(empty0 + (uint32_t)stage * 8);    // both CTAs: shared-memory stage reusable
+          tcgen05_commit_mc2_elect(afree0 + (uint32_t)slot * 8);     // both CTAs: TMEM A slot (and its ready barrier) reusable
+          if (++stage == STAGES) stage = 0;
+          if (++slot == A_SLOTS) { slot = 0; sphase ^= 1; }
+        }
+        tcgen05_commit_mc2_elect(tfull0 + (uint32_t)acc * 8);        // both CTAs: accumulator complete -> epilogue
+      }
+    }
+  } else if (warp < 6) {
+    // ======================= A split -> TMEM (own 128 rows) =======================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    int stage = 0; uint32_t phase = 0;
+    int slot = 0; uint32_t sphase = 0;
+    const uint32_t ready_leader = mapa_u32(smem_u32(&ready[0]), 0);
+    for (int w = cluster_id; w < n_work; w += n_clusters) {
+      int kb_beg, kb_end;
+      k_range(w, kb_beg, kb_end);
+      float csum = 0.f;
+      for (int kb = kb_beg; kb < kb_end; kb += KSUB) {
+        mbar_wait(&full_bar[stage], phase);
+        const int nsub = min(KSUB, kb_end - kb);
+        for (int j = 0; j < nsub; ++j) {
+          const uint8_t* sa = smem + stage * STAGE_BYTES + j * SUB_BYTES;
+          uint32_t hi[32], lo[32];
+          if (!TN) {
+            // K-major tile, 128B swizzle: row r at r * 128, 16-byte chunk c stored at chunk c ^ (r & 7)
+            const uint8_t* row = sa + r * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 x = *reinterpret_cast<const float4*>(row + ((c ^ (r & 7)) << 4));
+              hi[4 * c + 0] = __float_as_uint(x.x); hi[4 * c + 1] = __float_as_uint(x.y);
+              hi[4 * c + 2] = __float_as_uint(x.z); hi[4 * c + 3] = __float_as_uint(x.w);
+            }
+          } else {
+            // MN-major boxes [32 node rows][32 features], SWIZZLE_128B_ATOM_32B: box q holds this warp's 32
+            // features; node row k at k * 128, 32-byte unit u stored at unit u ^ (k & 3)
+            const uint8_t* box = sa + q * 4096 + (lane & 7) * 4;
+            const int u = lane >> 3;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const float x = *reinterpret_cast<const float*>(box + k * 128 + ((u ^ (k & 3)) << 5));
+              hi[k] = __float_as_uint(x);
+              csum += x;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) lo[i] = __float_as_uint(tf32_lo(__uint_as_float(hi[i])));
+          if (j == 0) {
+            mbar_wait(&a_free[slot], sphase ^ 1);      // the MMAs that read this TMEM slot have retired
+            tcgen05_fence_after();
+          }
+          const uint32_t t_a = tmem_base + ((uint32_t)(q * 32) << 16) + L::A_COL0 + (uint32_t)(slot * KSUB + j) * 64;
+          tmem_st_32x32b_x32(t_a, hi);
+          tmem_st_32x32b_x32(t_a + 32, lo);
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(ready_leader + (uint32_t)slot * 8);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++slot == A_SLOTS) { slot = 0; sphase ^= 1; }
+      }
+      if (TN && p.colsum_partial) {
+        const int split = w % p.splits, tile = w / p.splits;
+        const int m = (tile / p.tiles_n) * (2 * BM) + (int)rank * BM + r;
+        if (tile % p.tiles_n == 0 && m < p.M) p.colsum_partial[(int64_t)split * p.M + m] = csum;
+      }
+    }
+  } else if (warp < 10) {
+    // ======================= B split in shared memory (own half of the N rows) =======================
+    const int t = threadIdx.x - 6 * 32;
+    const int n_vec = half_bn * BK * 4 / 16;
+    int stage = 0; uint32_t phase = 0;
+    int slot = 0; uint32_t sphase = 0;
+    const uint32_t ready_leader = mapa_u32(smem_u32(&ready[0]), 0);
+    for (int w = cluster_id; w < n_work; w += n_clusters) {
+      int kb_beg, kb_end;
+      k_range(w, kb_beg, kb_end);
+      for (int kb = kb_beg; kb < kb_end; kb += KSUB) {
+        mbar_wait(&full_bar[stage], phase);
+        const int nsub = min(KSUB, kb_end - kb);
+        {
+          for (int j = 0; j < nsub; ++j) {
+            const float4* hi = reinterpret_cast<const float4*>(smem + stage * STAGE_BYTES + j * SUB_BYTES + A_STAGE_BYTES);
+            float4* lo = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES + j * SUB_BYTES + A_STAGE_BYTES + L::B_HALF_BYTES);
+#pragma unroll 4
+            for (int i = t; i < n_vec; i += 128) {
+              const float4 x = hi[i];
+              lo[i] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+        // the ready barrier is per A slot: do not arrive for round i before the phase of round i - A_SLOTS is over
+        mbar_wait(&a_free[slot], sphase ^ 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(ready_leader + (uint32_t)slot * 8);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++slot == A_SLOTS) { slot = 0; sphase ^= 1; }
+      }
+    }
+  } else {
+    // ======================= epilogue warps (own 128 rows of C) =======================
+    const int ew = warp - 10;
+    const int q = warp & 3;
+    float* stg = epi_stage + ew * 32 * EPI_LD;
+    const bool masked = !TN && p.act == GTS_ACT_MASK_POS;
+    const uint32_t tmem_empty_leader = mapa_u32(smem_u32(&tmem_empty[0]), 0);
+    int it = 0;
+    for (int w = cluster_id; w < n_work; w += n_clusters, ++it) {
+      int tile = w, split = 0;
+      if (TN) { split = w % p.splits; tile = w / p.splits; }
+      const int m0 = (tile / p.tiles_n) * (2 * BM) + (int)rank * BM + q * 32;
+      const int n0 = (tile % p.tiles_n) * p.BN;
+      float* Cout = p.C + (TN ? (int64_t)split * p.split_stride : 0);
+      const int acc = it % ACC_BUFS;
+      const uint32_t t_base = tmem_base + (uint32_t)acc * L::BN_MAX + ((uint32_t)(q * 32) << 16);
+      epilogue_tile<TN>(p, t_base, m0, n0, Cout, stg, lane, 0, 32, masked, &tmem_full[acc], (uint32_t)(it / ACC_BUFS) & 1);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(tmem_empty_leader + (uint32_t)acc * 8);
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();                                // no CTA may exit (or free TMEM) while its peer still uses it
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -808,6 +1209,31 @@ static int launch_ts(const CUtensorMap& a1, const CUtensorMap& a2, const CUtenso
   return GTS_OK;
 }
 
+template <bool TN>
+static int launch_ts2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1, const CUtensorMap& b2,
+                      const Params& p, int n_work, cudaStream_t st) {
+  using L = Ts2Cfg;
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_x3ts2_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::dyn_bytes);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d) failed: %s", L::dyn_bytes, cudaGetErrorString(e)); return GTS_ERR_CUDA; }
+    done = true;
+  }
+  const int pairs = sm_count() / 2;
+  const int grid = 2 * (n_work < pairs ? n_work : pairs);          // one CTA pair (cluster of 2) per TPC
+  gemm_x3ts2_kernel<TN><<<grid, L::THREADS, L::dyn_bytes, st>>>(a1, a2, b1, b2, p);
+  GTS_LAUNCH_CHECK();
+  return GTS_OK;
+}
+
+// CTA-pair (cta_group::2) form for the wide shapes; GTS_X3_CTAS=1 keeps every shape on the one-CTA kernel
+static bool ts_pair_enabled() {
+  static const bool off = getenv("GTS_X3_CTAS") && atoi(getenv("GTS_X3_CTAS")) == 1;
+  return !off;
+}
+static bool nt_pair_shape(int M, int N) { return ts_pair_enabled() && M >= 256 && N >= 128 && N % 64 == 0; }
+static bool tn_pair_shape(int Mo, int No) { return ts_pair_enabled() && Mo > 128 && No >= 128 && No % 64 == 0; }
+
 // widest N tile of the A-in-TMEM kernel: 128 (default: 4 stages, overlapped epilogue) or 256 (GTS_X3_BN=256)
 static int ts_bn_cap() {
   static const int cap = (getenv("GTS_X3_BN") && atoi(getenv("GTS_X3_BN")) == 256) ? 256 : 128;
@@ -845,9 +1271,10 @@ int gemm_nt_tcgen05(const gts_gemm_nt_args* a, cudaStream_t st) {
   const bool rnd = !x3;      // 1xTF32: TMA rounds to nearest; 3xTF32: raw fp32 (the MMA truncates, lo = x - trunc(x))
   const bool two = a->A2 && a->B2 && a->K2 > 0;
   const bool in_tmem = x3 && x3_in_tmem();
+  const bool pair = in_tmem && nt_pair_shape(a->M, a->N);
   Params p{};
-  p.BN = pick_bn(a->N, 16, in_tmem ? ts_bn_cap() : MAX_BN);
-  p.tiles_m = (a->M + BM - 1) / BM;
+  p.BN = pair ? pick_bn(a->N, 64, Ts2Cfg::BN_MAX) : pick_bn(a->N, 16, in_tmem ? ts_bn_cap() : MAX_BN);
+  p.tiles_m = pair ? (a->M + 2 * BM - 1) / (2 * BM) : (a->M + BM - 1) / BM;
   p.tiles_n = (a->N + p.BN - 1) / p.BN;
   p.M = a->M; p.N = a->N; p.C = a->C; p.ldc = a->ldc;
   p.kb1 = (a->K1 + BK - 1) / BK;
@@ -856,14 +1283,16 @@ int gemm_nt_tcgen05(const gts_gemm_nt_args* a, cudaStream_t st) {
   p.splits = 1;
   CUtensorMap tA1, tA2, tB1, tB2;
   if (!encode_2d(&tA1, a->A1, a->M, a->K1, a->lda1, BK, BM, rnd)) return GTS_ERR_CUDA;
-  if (!encode_2d(&tB1, a->B1, a->N, a->K1, a->ldb1, BK, p.BN, rnd)) return GTS_ERR_CUDA;
+  const int b_rows = pair ? p.BN / 2 : p.BN;        // a CTA pair lands half of the N rows per CTA
+  if (!encode_2d(&tB1, a->B1, a->N, a->K1, a->ldb1, BK, b_rows, rnd)) return GTS_ERR_CUDA;
   if (two) {
     if (!encode_2d(&tA2, a->A2, a->M, a->K2, a->lda2, BK, BM, rnd)) return GTS_ERR_CUDA;
-    if (!encode_2d(&tB2, a->B2, a->N, a->K2, a->ldb2, BK, p.BN, rnd)) return GTS_ERR_CUDA;
+    if (!encode_2d(&tB2, a->B2, a->N, a->K2, a->ldb2, BK, b_rows, rnd)) return GTS_ERR_CUDA;
   } else {
     tA2 = tA1; tB2 = tB1;
   }
   const int n_work = p.tiles_m * p.tiles_n;
+  if (pair) return launch_ts2<false>(tA1, tA2, tB1, tB2, p, n_work, st);
   if (in_tmem)
     return ts_bn_cap() == 256 ? launch_ts<false, 256>(tA1, tA2, tB1, tB2, p, n_work, st)
                               : launch_ts<false, 128>(tA1, tA2, tB1, tB2, p, n_work, st);
@@ -879,12 +1308,14 @@ bool gemm_tn_tcgen05_supported(const float* A, int64_t lda, const float* B, int6
 
 static void tn_plan(int32_t Mo, int32_t No, int64_t K, int32_t mode, tc::Params& p) {
   using namespace tc;
-  p.BN = pick_bn(No, 32, (mode == GTS_GEMM_TF32X3 && x3_in_tmem()) ? ts_bn_cap() : MAX_BN);
-  p.tiles_m = (Mo + BM - 1) / BM;
+  const bool in_tmem = mode == GTS_GEMM_TF32X3 && x3_in_tmem();
+  const bool pair = in_tmem && tn_pair_shape(Mo, No);
+  p.BN = pair ? pick_bn(No, 64, Ts2Cfg::BN_MAX) : pick_bn(No, 32, in_tmem ? ts_bn_cap() : MAX_BN);
+  p.tiles_m = pair ? (Mo + 2 * BM - 1) / (2 * BM) : (Mo + BM - 1) / BM;
   p.tiles_n = (No + p.BN - 1) / p.BN;
   p.kb_total = (int)((K + BK - 1) / BK);
   const int tiles = p.tiles_m * p.tiles_n;
-  int splits = sm_count() / tiles;
+  int splits = (pair ? sm_count() / 2 : sm_count()) / tiles;
   if (splits < 1) splits = 1;
   if (splits > p.kb_total) splits = p.kb_total;
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
@@ -924,7 +1355,9 @@ int gemm_tn_tcgen05(const float* A, int64_t lda, const float* B, int64_t ldb, fl
   if (!encode_2d(&tA, A, K, Mo, lda, 32, BK, !x3, true)) return GTS_ERR_CUDA;
   if (!encode_2d(&tB, B, K, No, ldb, 32, BK, !x3, true)) return GTS_ERR_CUDA;
   const int n_work = p.tiles_m * p.tiles_n * p.splits;
-  int rc = in_tmem ? (ts_bn_cap() == 256 ? launch_ts<true, 256>(tA, tA, tB, tB, p, n_work, st)
+  const bool pair = in_tmem && tn_pair_shape(Mo, No);
+  int rc = pair ? launch_ts2<true>(tA, tA, tB, tB, p, n_work, st)
+         : in_tmem ? (ts_bn_cap() == 256 ? launch_ts<true, 256>(tA, tA, tB, tB, p, n_work, st)
                                          : launch_ts<true, 128>(tA, tA, tB, tB, p, n_work, st))
                    : (x3 ? launch<true, true>(tA, tA, tB, tB, p, n_work, st) : launch<true, false>(tA, tA, tB, tB, p, n_work, st));
   if (rc != GTS_OK) return rc;

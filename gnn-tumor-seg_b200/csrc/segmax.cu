@@ -133,8 +133,11 @@ segmax_fwd_wide_kernel(const float* __restrict__ P, int64_t ldp, const int32_t* 
   const int64_t v_begin = (int64_t)blockIdx.x * nodes_per_cta;
   const int64_t v_end = v_begin + nodes_per_cta < N ? v_begin + nodes_per_cta : N;
   const int slab4 = blockIdx.y * 32 * VEC;       // gridDim.y column slabs of 128*VEC floats each
-  const float4* __restrict__ Pl = reinterpret_cast<const float4*>(P) + slab4 + lane;
-  const uint32_t ld4 = (uint32_t)(ldp >> 2);     // host guarantees N * ld4 < 2^31: 32-bit row offsets
+  const char* __restrict__ Pl = reinterpret_cast<const char*>(reinterpret_cast<const float4*>(P) + slab4 + lane);
+  const uint32_t ld_bytes = (uint32_t)(ldp << 2);   // host guarantees N * ldp * 4 < 2^32: one IMAD.WIDE per row address
+  auto row_of = [&](int32_t u) {
+    return reinterpret_cast<const float4*>(Pl + (uint64_t)(uint32_t)u * ld_bytes);
+  };
 
   for (int64_t v = v_begin + warp; v < v_end; v += kWideWarps) {
     const int32_t beg = indptr[v], end = indptr[v + 1];
@@ -147,15 +150,16 @@ segmax_fwd_wide_kernel(const float* __restrict__ P, int64_t ldp, const int32_t* 
     }
     for (int32_t base = beg; base < end; base += 32) {
       const int32_t my_idx = (base + lane < end) ? indices[base + lane] : 0;
-      const int32_t cnt = min(32, end - base);
-      int32_t j = 0;
-      for (; j + 4 <= cnt; j += 4) {
-        const int32_t u0 = __shfl_sync(full, my_idx, j), u1 = __shfl_sync(full, my_idx, j + 1);
-        const int32_t u2 = __shfl_sync(full, my_idx, j + 2), u3 = __shfl_sync(full, my_idx, j + 3);
-        const float4* p0 = Pl + (uint32_t)u0 * ld4;
-        const float4* p1 = Pl + (uint32_t)u1 * ld4;
-        const float4* p2 = Pl + (uint32_t)u2 * ld4;
-        const float4* p3 = Pl + (uint32_t)u3 * ld4;
+      const int32_t last = min(32, end - base) - 1;
+      // whole groups of four; a short last group repeats the row's last neighbour, which can never win
+      // again (strictly-greater test), so the loop body has no per-neighbour predicate at all
+      for (int32_t j = 0; j <= last; j += 4) {
+        const int32_t u0 = __shfl_sync(full, my_idx, j), u1 = __shfl_sync(full, my_idx, min(j + 1, last));
+        const int32_t u2 = __shfl_sync(full, my_idx, min(j + 2, last)), u3 = __shfl_sync(full, my_idx, min(j + 3, last));
+        const float4* p0 = row_of(u0);
+        const float4* p1 = row_of(u1);
+        const float4* p2 = row_of(u2);
+        const float4* p3 = row_of(u3);
         float4 r0[VEC], r1[VEC], r2[VEC], r3[VEC];
 #pragma unroll
         for (int c = 0; c < VEC; ++c) { r0[c] = ldg_nc(p0 + 32 * c); r1[c] = ldg_nc(p1 + 32 * c); }
@@ -168,15 +172,6 @@ segmax_fwd_wide_kernel(const float* __restrict__ P, int64_t ldp, const int32_t* 
           fold_max(best[c], arg[c], r2[c], u2);
           fold_max(best[c], arg[c], r3[c], u3);
         }
-      }
-      for (; j < cnt; ++j) {
-        const int32_t u0 = __shfl_sync(full, my_idx, j);
-        const float4* p0 = Pl + (uint32_t)u0 * ld4;
-        float4 r0[VEC];
-#pragma unroll
-        for (int c = 0; c < VEC; ++c) r0[c] = ldg_nc(p0 + 32 * c);
-#pragma unroll
-        for (int c = 0; c < VEC; ++c) fold_max(best[c], arg[c], r0[c], u0);
       }
     }
 #pragma unroll
@@ -192,9 +187,9 @@ segmax_fwd_wide_kernel(const float* __restrict__ P, int64_t ldp, const int32_t* 
 template <int VEC, int kWideWarps>
 static int launch_fwd_wide(const float* P, int64_t ldp, const int32_t* indptr, const int32_t* indices, int32_t N,
                            float* neigh, int64_t ldn, int32_t* argmax, int64_t ldarg, cudaStream_t st, int slabs = 1) {
+  // one CTA per SM, contiguous id ranges of (almost) equal length
   int64_t grid = sm_count();
-  int64_t per_cta = ceil_div<int64_t>(N, grid);
-  per_cta = ceil_div<int64_t>(per_cta, kWideWarps) * kWideWarps;
+  const int64_t per_cta = ceil_div<int64_t>(N, grid);
   grid = ceil_div<int64_t>(N, per_cta);
   if (argmax)
     segmax_fwd_wide_kernel<VEC, true, kWideWarps><<<dim3((unsigned)grid, slabs), kWideWarps * 32, 0, st>>>(P, ldp, indptr, indices, N, neigh, ldn, argmax, ldarg, per_cta);
@@ -379,7 +374,7 @@ int gts_segmax_fwd(const float* P, int64_t ldp, const int32_t* indptr, const int
                       aligned16(P) && aligned16(neigh) && (!argmax || aligned16(argmax)) && D <= 1024;
   static const bool no_wide = getenv("GTS_SEGMAX_GENERIC") != nullptr;   // A/B switch for profiling
   static const int wide_warps = getenv("GTS_SEGMAX_WARPS") ? atoi(getenv("GTS_SEGMAX_WARPS")) : 32;
-  const bool wide_ok = !no_wide && vec_ok && (int64_t)n_nodes * (ldp / 4) < ((int64_t)1 << 31);
+  const bool wide_ok = !no_wide && vec_ok && (int64_t)n_nodes * ldp * 4 < ((int64_t)1 << 32);
   if (wide_ok && D == 128) return launch_fwd_wide<1, 32>(P, ldp, indptr, indices, n_nodes, neigh, ldn, argmax, ldarg, st);
   if (wide_ok && D == 256) {
     if (wide_warps == 48) return launch_fwd_wide<1, 24>(P, ldp, indptr, indices, n_nodes, neigh, ldn, argmax, ldarg, st, 2);
