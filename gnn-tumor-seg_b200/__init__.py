@@ -19,7 +19,9 @@ _LAZY = {
     "BatchedGraph": "graph", "minibatch_graphs": "graph", "from_networkx": "graph",
     "batch": "graph", "from_edge_list": "graph",
     "project_nodes_to_img": "project", "project_labels_to_brats": "project",
-    "project_logits_to_img": "project",
+    "project_logits_to_img": "project", "determine_tumor_crop": "project",
+    "ImageGraphDataset": "data_loader", "PredLogitDataset": "data_loader",
+    "load_graph_json": "graph_io", "parse_node_link_json": "graph_io",
 }
 
 

@@ -98,6 +98,8 @@ _SIGNATURES = {
     "gts_project_labels": (C.c_int, [c_i16p, C.c_int32, C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p, c_i32p,
                                      C.c_int32, c_i16p, C.c_int32, c_i16p, C.c_int32, C.c_int32, C.c_int32,
                                      c_i32p, c_stream]),
+    "gts_tumor_plane_occupancy": (C.c_int, [c_i16p, C.c_int32, C.c_int32, C.c_int32, c_i32p, C.c_int32, c_i32p, c_i32p,
+                                            c_i32p, c_i32p, c_stream]),
     "gts_project_logits": (C.c_int, [c_i16p, C.c_int64, c_f32p, C.c_int64, C.c_int32, C.c_int32, c_f32p, c_f32p,
                                      c_i32p, c_stream]),
     "gts_gat_scores": (C.c_int, [c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, c_f32p,

@@ -36,6 +36,34 @@ __global__ void project_nodes_kernel(const int16_t* __restrict__ svs, int64_t n_
   }
 }
 
+// determine_tumor_crop (data_processing/image_processing.py:8-17) without materialising the voxel predictions:
+// a voxel is "tumour" when its supervoxel's class is non-zero (background -1 -> healthy).  The crop the
+// reference returns is np.ix_ of the planes that contain a voxel of binary_dilation(mask) (3-D cross, one step,
+// border 0) — and a plane contains such a voxel iff it or one of its two neighbour planes contains a tumour
+// voxel.  So one pass marks plane occupancy (one warp-level vote, then at most one atomicOr per warp and axis
+// plane), the +-1 dilation of three short vectors is host-side arithmetic on 536 flags.
+__global__ void __launch_bounds__(256)
+plane_occupancy_kernel(const int16_t* __restrict__ svs, int32_t X, int32_t Y, int32_t Z,
+                       const int32_t* __restrict__ node_cls, int32_t N,
+                       int32_t* __restrict__ occ_x, int32_t* __restrict__ occ_y, int32_t* __restrict__ occ_z,
+                       int32_t* __restrict__ err) {
+  const int64_t total = (int64_t)X * Y * Z;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t s = svs[i];
+    bool tumour = false;
+    if (s >= 0 && s < N) tumour = node_cls[s] != 0;
+    else if (s != -1) *err = 1;
+    if (tumour) {
+      const int32_t z = (int32_t)(i % Z);
+      const int64_t t = i / Z;
+      // idempotent flags: plain stores race benignly (every writer stores 1)
+      occ_z[z] = 1;
+      occ_y[(int32_t)(t % Y)] = 1;
+      occ_x[(int32_t)(t / Y)] = 1;
+    }
+  }
+}
+
 // One thread per 8 consecutive output voxels (one 16-byte store).  The flat
 // output index is decomposed once, then walked along z with carries.
 __global__ void __launch_bounds__(256)
@@ -161,6 +189,28 @@ int gts_project_logits(const int16_t* svs, int64_t n_vox, const float* node_logi
   GTS_CHECK_ARG(svs && bg_row && out && err_flag && (node_logits || n_nodes == 0), "gts_project_logits: null pointer");
   project_logits_kernel<<<pj_grid(n_vox * n_classes, 256), 256, 0, as_stream(stream)>>>(svs, n_vox, node_logits, ld, n_nodes,
                                                                                       n_classes, bg_row, out, err_flag);
+  GTS_LAUNCH_CHECK();
+  return GTS_OK;
+}
+
+int gts_tumor_plane_occupancy(const int16_t* svs, int32_t X, int32_t Y, int32_t Z,
+                              const int32_t* node_cls, int32_t n_nodes,
+                              int32_t* occ_x, int32_t* occ_y, int32_t* occ_z,
+                              int32_t* err_flag, gts_stream_t stream) {
+  GTS_CHECK_ARG(X >= 0 && Y >= 0 && Z >= 0 && n_nodes >= 0, "gts_tumor_plane_occupancy: negative size");
+  GTS_CHECK_ARG(occ_x && occ_y && occ_z && err_flag, "gts_tumor_plane_occupancy: null output");
+  cudaStream_t st = as_stream(stream);
+  if (X > 0) GTS_CUDA(cudaMemsetAsync(occ_x, 0, sizeof(int32_t) * X, st));
+  if (Y > 0) GTS_CUDA(cudaMemsetAsync(occ_y, 0, sizeof(int32_t) * Y, st));
+  if (Z > 0) GTS_CUDA(cudaMemsetAsync(occ_z, 0, sizeof(int32_t) * Z, st));
+  const int64_t total = (int64_t)X * Y * Z;
+  if (total == 0) return GTS_OK;
+  GTS_CHECK_ARG(svs && (node_cls || n_nodes == 0), "gts_tumor_plane_occupancy: null input");
+  int64_t blocks = ceil_div<int64_t>(total, 256 * 8);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  plane_occupancy_kernel<<<(int)blocks, 256, 0, st>>>(svs, X, Y, Z, node_cls, n_nodes, occ_x, occ_y, occ_z, err_flag);
   GTS_LAUNCH_CHECK();
   return GTS_OK;
 }

@@ -1,0 +1,117 @@
+"""Dataset side of the hot path with the reference's entry points
+(data_processing/data_loader.py:39-169): ``ImageGraphDataset`` (graph part),
+``PredLogitDataset.get_crop`` and ``minibatch_graphs``.
+
+``get_graph`` returns ``(graph, features, labels)`` like the reference, with a
+host ``BatchedGraph`` in place of the DGLGraph: the node-link JSON is parsed
+once per file into the arrays the device CSR build consumes and cached in
+binary form (graph_io.load_graph_json) instead of being re-parsed into networkx
+and DGL objects for every sample of every epoch.
+
+NIfTI files (images, voxel labels, supervoxel maps) are outside the hot path
+(nibabel is absent from this image): the accessors read ``.npy``
+twins when they exist and raise otherwise.
+"""
+from __future__ import annotations
+
+import glob
+import os
+
+import numpy as np
+import torch
+
+from . import graph_io
+from ._lib import GtsError
+from .graph import minibatch_graphs  # noqa: F401  (collate_fn, data_loader.py:165-169)
+from .project import determine_tumor_crop
+
+
+class ImageGraphDataset(torch.utils.data.Dataset):
+    """data_processing/data_loader.py:39-120."""
+
+    def __init__(self, dataset_root_dir, mri_start_string, read_image=True, read_graph=True, read_label=True):
+        self.dataset_root_dir = dataset_root_dir
+        self.all_ids = self.get_all_mris_in_dataset(dataset_root_dir, mri_start_string)
+        self.read_image = read_image
+        self.read_graph = read_graph
+        self.read_label = read_label
+        assert (self.read_graph or self.read_image)
+
+    def get_all_mris_in_dataset(self, dataset_root_dir, mri_start_string):
+        mri_folders = glob.glob(f"{dataset_root_dir}**/{mri_start_string}*/", recursive=True)
+        mri_ids = [fp.split(os.sep)[-2] for fp in mri_folders]
+        print(f"Found {len(mri_folders)} MRIs")
+        return mri_ids
+
+    def get_one(self, mri_id):
+        if self.read_graph and not self.read_image:
+            return (mri_id, *self.get_graph(mri_id))
+        elif self.read_image and not self.read_graph:
+            return (mri_id, *self.get_image(mri_id))
+        elif self.read_image and self.read_graph:
+            return (mri_id, *self.get_graph(mri_id), *self.get_image(mri_id))
+        else:
+            print("Invalid combination of flags")
+
+    def _path(self, mri_id, suffix):
+        return f"{self.dataset_root_dir}{os.sep}{mri_id}{os.sep}{mri_id}{suffix}"
+
+    def get_graph(self, mri_id):
+        """data_loader.py:67-83.  The 'norm' node field the reference computes there is never read by
+        any network and is not produced."""
+        G, features, labels = graph_io.load_graph_json(self._path(mri_id, "_nxgraph.json"))
+        if self.read_label:
+            return G, features, labels
+        return G, features
+
+    def _read_volume(self, mri_id, stem, dtype):
+        fp = self._path(mri_id, stem + ".npy")
+        if os.path.exists(fp):
+            return np.load(fp).astype(dtype, copy=False)
+        raise GtsError(f"{self._path(mri_id, stem + '.nii.gz')}: NIfTI I/O is outside the hot path of this package "
+                       f"(nibabel is not available); provide {fp}")
+
+    def get_voxel_labels(self, mri_id):
+        return self._read_volume(mri_id, "_label", np.int16)
+
+    def get_image(self, mri_id):
+        img = self._read_volume(mri_id, "_input", np.float32)
+        if self.read_label:
+            return img, self.get_voxel_labels(mri_id)
+        return (img,)
+
+    def get_supervoxel_partitioning(self, mri_id):
+        return self._read_volume(mri_id, "_supervoxels", np.int16)
+
+    def get_crop(self, mri_id):
+        return tuple(np.load(self._path(mri_id, "_crop.npy"), allow_pickle=True))
+
+    def __iter__(self):
+        for mri_id in self.all_ids:
+            yield self.get_one(mri_id)
+
+    def __getitem__(self, index):
+        return self.get_one(self.all_ids[index])
+
+    def __len__(self):
+        return len(self.all_ids)
+
+
+class PredLogitDataset:
+    """data_processing/data_loader.py:138-165: cached tumour crops of saved GNN logits.  ``get_crop`` here takes
+    the supervoxel map and node logits / classes and runs the plane-occupancy kernel; the reference computes the
+    same crop from the saved voxel-logit volume."""
+
+    def __init__(self, root_dir=None):
+        self.root_dir = root_dir
+        self.mri_crops = {}
+
+    def get_crop(self, mri_id, svs=None, node_logits=None):
+        if mri_id in self.mri_crops:
+            return self.mri_crops[mri_id]
+        if svs is None or node_logits is None:
+            raise GtsError("PredLogitDataset.get_crop: pass the supervoxel map and the node logits on first use "
+                           "(saved NIfTI logit volumes are outside the hot path)")
+        crop_idxs = determine_tumor_crop(svs, node_logits)
+        self.mri_crops[mri_id] = crop_idxs
+        return crop_idxs

@@ -136,3 +136,45 @@ def project_logits_to_img(node_logits, svs, background=DEFAULT_BACKGROUND_NODE_L
                                      ptr(out), ptr(err), stream_ptr()), "gts_project_logits")
     out._gts_err = err
     return out
+
+
+def determine_tumor_crop(svs, node_classes_or_logits):
+    """determine_tumor_crop (data_processing/image_processing.py:8-17) for the GNN's own predictions, without
+    building the voxel prediction volume: the crop the reference computes from
+    ``node_logits[svs].argmax(-1)`` (scripts/generate_joint_predictions.py:64-67; PredLogitDataset.get_crop,
+    data_processing/data_loader.py:146-151) depends only on which planes of the supervoxel map hold a
+    predicted-tumour voxel.  Returns the same ``np.ix_`` tuple of int64 index arrays."""
+    lib = _lib.load()
+    x = node_classes_or_logits
+    dev = x.device if (torch.is_tensor(x) and x.is_cuda) else _device()
+    svs_d = _as_dev(svs, torch.int16, dev)
+    if svs_d.dim() != 3:
+        raise ValueError("svs must be the 3-D supervoxel map")
+    X, Y, Z = (int(v) for v in svs_d.shape)
+    with torch.cuda.device(dev):
+        st = stream_ptr()
+        xt = x if torch.is_tensor(x) else torch.as_tensor(np.ascontiguousarray(x))
+        if xt.dim() == 2:
+            logits = xt.to(device=dev, dtype=torch.float32).contiguous()
+            cls = torch.empty(logits.shape[0], dtype=torch.int32, device=dev)
+            check(lib.gts_argmax_rows(ptr(logits), logits.stride(0), logits.shape[0], logits.shape[1], ptr(cls), st),
+                  "gts_argmax_rows")
+        else:
+            cls = xt.to(device=dev, dtype=torch.int32).contiguous()
+        occ = torch.empty(X + Y + Z, dtype=torch.int32, device=dev)
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        check(lib.gts_tumor_plane_occupancy(ptr(svs_d), X, Y, Z, ptr(cls), cls.numel(), ptr(occ), ptr(occ[X:]),
+                                            ptr(occ[X + Y:]), ptr(err), st), "gts_tumor_plane_occupancy")
+    host = torch.cat([occ, err]).cpu().numpy()          # one device->host read: 3 short flag vectors + the error flag
+    if host[-1]:
+        raise IndexError(f"supervoxel id out of bounds for {cls.numel()} nodes")
+    flags = []
+    for a, b in ((0, X), (X, X + Y), (X + Y, X + Y + Z)):
+        o = host[a:b].astype(bool)
+        d = o.copy()                                      # one step of binary dilation along the axis, border 0
+        d[1:] |= o[:-1]
+        d[:-1] |= o[1:]
+        flags.append(d)
+    if not any(f.any() for f in flags):                   # nothing predicted tumorous: the whole (uncropped) volume
+        flags = [np.ones(n, dtype=bool) for n in (X, Y, Z)]
+    return np.ix_(*flags)

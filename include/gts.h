@@ -269,6 +269,17 @@ GTS_API int gts_project_labels(const int16_t* svs, int32_t X, int32_t Y, int32_t
                        int16_t* vol, int32_t VX, int32_t VY, int32_t VZ,
                        int32_t* err_flag, gts_stream_t stream);
 
+/* determine_tumor_crop (data_processing/image_processing.py:8-17; used by
+ * scripts/generate_joint_predictions.py:67 and data_loader.py PredLogitDataset.get_crop:148-150):
+ * occ_x[x] = 1 iff plane x of the cropped map holds a voxel whose supervoxel class is non-zero
+ * (same for y, z; background -1 counts as healthy).  The reference's crop = planes whose occupancy,
+ * dilated by one plane on each side (scipy binary_dilation, 3-D cross), is set; all planes when
+ * nothing is predicted tumorous.  err_flag set to 1 on an id outside [-1,n_nodes). */
+GTS_API int gts_tumor_plane_occupancy(const int16_t* svs, int32_t X, int32_t Y, int32_t Z,
+                              const int32_t* node_cls, int32_t n_nodes,
+                              int32_t* occ_x, int32_t* occ_y, int32_t* occ_z,
+                              int32_t* err_flag, gts_stream_t stream);
+
 /* save_voxel_logits (scripts/generate_gnn_predictions.py:55-62;
  * scripts/generate_joint_predictions.py:64-66): out[i,:] = svs[i]==-1 ?
  * bg_row : node_logits[svs[i],:]. */

@@ -52,3 +52,15 @@ def save_voxel_logits_ref(node_logits, svs):
     fancy-indexed by the supervoxel map -> float [X,Y,Z,C]."""
     node_logits = np.concatenate([np.asarray(node_logits), DEFAULT_BACKGROUND_NODE_LOGITS])
     return node_logits[svs]
+
+
+def determine_tumor_crop_ref(preds):
+    """data_processing/image_processing.py:8-17: dilate the predicted-tumour mask by one 3-D cross step
+    (scipy.ndimage.binary_dilation defaults) and keep the planes that hold a voxel of it; the whole volume
+    when nothing is predicted tumorous."""
+    from scipy import ndimage
+    mask = np.asarray(preds) != 0
+    mask = ndimage.binary_dilation(mask)
+    if np.all(~mask):
+        mask = ~mask
+    return np.ix_(mask.any(axis=(1, 2)), mask.any(axis=(0, 2)), mask.any(axis=(0, 1)))

@@ -120,6 +120,32 @@ def main():
         vox_brats_dtype=str(vox_brats.dtype), vox_dtype=str(vox.dtype), proj_dtype=str(proj.dtype),
         vox_logits=vox_logits, swapped=swapped, swap_error=raised,
     )
+    # 5. determine_tumor_crop (data_processing/image_processing.py:8-17) on the projected predictions, on an
+    #    all-healthy volume, and on tumour voxels touching the volume border; and the node-link JSON text the
+    #    reference's save_networkx_graph writes (the on-disk graph format, data_processing/graph_io.py:27-37)
+    crops = {}
+    cases = {"pred": vox, "healthy": np.zeros_like(vox)}
+    edge = np.zeros((9, 7, 5), dtype=np.int64)
+    edge[0, 3, 2] = 2
+    edge[8, 6, 4] = 1
+    edge[4, 0, 0] = 3
+    cases["border"] = edge
+    sparse = np.zeros((12, 10, 8), dtype=np.int64)
+    sparse[5, 4, 3] = 1
+    cases["single"] = sparse
+    for name, vol in cases.items():
+        cx = image_processing.determine_tumor_crop(vol)
+        for a in range(3):
+            crops[f"tcrop_{name}_{a}"] = np.asarray(cx[a]).reshape(-1)
+        crops[f"tcrop_{name}_vol"] = vol
+    with tempfile.TemporaryDirectory() as td:
+        fp = os.path.join(td, "g_nxgraph.json")
+        graph_io.save_networkx_graph(G, fp)
+        json_text = open(fp).read()
+    np.savez_compressed(os.path.join(OUT, "reference_kat_crop.npz"), json_text=np.frombuffer(json_text.encode(), dtype=np.uint8),
+                        **crops)
+    print("wrote", os.path.join(OUT, "reference_kat_crop.npz"), {k: v.shape for k, v in crops.items() if k.endswith("_0")})
+
     print("wrote", os.path.join(OUT, "reference_kat.npz"), "n3 =", n3, "edges =", len(r3),
           "nonzero voxels =", int((vox_brats != 0).sum()), "dtypes", vox.dtype, vox_brats.dtype, vox_logits.dtype)
 

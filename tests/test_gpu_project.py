@@ -70,3 +70,38 @@ def test_full_size_synthetic_volume(cuda_dev):
     for c, lab in enumerate(project.BRATS_LABEL_LUT):
         if lab:
             assert (vol == lab).sum() == counts[cls == c].sum()
+
+
+GOLD_CROP = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_kat_crop.npz"))
+
+
+@pytest.mark.parametrize("case", ["pred", "healthy", "border", "single"])
+def test_determine_tumor_crop_golden(cuda_dev, case):
+    """Plane-occupancy kernel vs the crops the reference's determine_tumor_crop returned
+    (tests/golden/make_golden.py): every voxel is its own supervoxel, its class = the predicted label."""
+    vol = GOLD_CROP[f"tcrop_{case}_vol"]
+    flat = vol.reshape(-1)
+    svs = np.arange(flat.size, dtype=np.int64).reshape(vol.shape)
+    if flat.size > 32767:
+        pytest.skip("fixture volume exceeds the int16 supervoxel id range")
+    ix = project.determine_tumor_crop(svs.astype(np.int16), flat.astype(np.int64))
+    for a in range(3):
+        assert np.array_equal(np.asarray(ix[a]).reshape(-1), GOLD_CROP[f"tcrop_{case}_{a}"])
+        assert ix[a].ndim == 3                                   # np.ix_ shape, usable as vol[ix]
+
+
+def test_determine_tumor_crop_full_size_vs_oracle(cuda_dev):
+    """Config-5 size: 15k-node partition, random node logits; crop == the oracle's crop of the voxel predictions."""
+    g = synth.make_graph(1, with_partition=True)
+    rng = np.random.default_rng(5)
+    logits = rng.normal(size=(g.n_nodes, 4)).astype(np.float32)
+    logits[:, 0] += 3.0                                          # mostly healthy, a few tumour supervoxels
+    ix = project.determine_tumor_crop(g.svs, torch.as_tensor(logits).to(cuda_dev))
+    ref = project_ref.determine_tumor_crop_ref(project_ref.project_nodes_to_img_ref(g.svs, logits.argmax(1)))
+    for a in range(3):
+        assert np.array_equal(ix[a], ref[a])
+    # nothing tumorous -> the whole volume
+    ix0 = project.determine_tumor_crop(g.svs, np.zeros(g.n_nodes, dtype=np.int64))
+    assert tuple(a.size for a in ix0) == g.svs.shape
+    with pytest.raises(IndexError):
+        project.determine_tumor_crop(np.full((2, 2, 2), 9, np.int16), np.array([1, 0]))
