@@ -45,6 +45,26 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
 
 
+def load_ncu_traffic():
+    """DRAM bytes per launch from the committed `ncu --set full` captures (tools/ncu_traffic.py ->
+    profiles/*_ncu_traffic.json).  Looked up by kernel-name substring; None when no capture exists."""
+    import glob
+    out = {}
+    for fp in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_traffic.json"))):
+        try:
+            out.update(json.load(open(fp)))
+        except Exception:
+            pass
+    return out
+
+
+def traffic_of(table, *needles):
+    for name, d in table.items():
+        if all(n in name for n in needles) and "dram_bytes" in d:
+            return d["dram_bytes"]
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -190,6 +210,8 @@ def kernel_breakdown(step_fn, ops):
     stack = ops.use_stack_path()
     try:
         ops.set_stack_path(False)          # per-layer path: same kernels, visible to the wrappers
+        step_fn()                          # warm the per-layer path (first-use attribute calls, allocator)
+        torch.cuda.synchronize()
         for n in names:
             setattr(ops, n, wrap(n))
         step_fn()
@@ -337,6 +359,10 @@ def run_ours(args):
                              "mma_passes": passes,
                              "peak_note": "TF32 dense peak taken as 1/2 of the measured sustained bf16 cuBLAS figure"},
     }
+    ncu = load_ncu_traffic()
+    kern["segmax_fwd"]["traffic"] = traffic_of(ncu, "segmax_fwd_wide")
+    kern["segmax_bwd"]["traffic"] = traffic_of(ncu, "segmax_bwd_vec")
+    kern["gemm_concat_k512"]["traffic"] = traffic_of(ncu, "gemm_x3ts2_kernel<0") if args.mode == "tf32x3" else None
     tot = sum(v["ms"] for v in breakdown.values()) or 1.0
     share = {k: {"ms": round(v["ms"], 4), "calls": v["calls"], "share": round(v["ms"] / tot, 4)}
              for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])}
@@ -346,13 +372,16 @@ def run_ours(args):
         flops = model_flops_bytes(n_nodes, n_edges)
         ach = flops / (gemm_ms * 1e-3) / 1e12
         roofline = {"kernel": "gemm (tcgen05 tf32)" if args.mode != "fp32" else "gemm (simt fp32)", "bound": "tensor",
-                    "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None,
-                    "note": "algorithmic fwd+bwd flops of the step / summed GEMM launch time in the step; "
-                            "peak = 1/2 measured sustained bf16 (%s)" % peaks["src"]}
+                    "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
+                    "traffic": kern["gemm_concat_k512"]["traffic"],
+                    "executed_tflops": ach * passes,
+                    "note": "algorithmic fwd+bwd flops of the step / summed GEMM launch time in the step (the tf32x3 mode "
+                            "executes 3 tensor-core passes per algorithmic flop: see executed_tflops); traffic = DRAM bytes of "
+                            "one concat-GEMM launch (ncu); peak = 1/2 measured sustained bf16 (%s)" % peaks["src"]}
     else:
         k = kern["segmax_fwd"]
         roofline = {"kernel": "segmax_fwd", "bound": "hbm", "achieved": k["achieved"], "peak": k["peak"],
-                    "unit": "GB/s", "frac": k["frac"], "traffic": None,
+                    "unit": "GB/s", "frac": k["frac"], "traffic": k.get("traffic"),
                     "note": "algorithmic bytes 4*(3*N*D + N+1 + E) / CUDA-event time; peak %s" % peaks["src"]}
 
     # ---- CPU baseline (oracle, bounded sample) ----
@@ -413,6 +442,123 @@ def run_ours(args):
         torch.distributed.destroy_process_group()
 
 
+
+# ---------------------------------------------------------------------------
+# BASELINE configs[4]: bulk inference of 1251 graphs + node->voxel reprojection (not the default workload)
+# ---------------------------------------------------------------------------
+def run_infer(args):
+    """One step = this rank's share of ``--infer-graphs`` MRIs (round-robin over ranks):
+    per-graph eval forward (as scripts/generate_gnn_predictions.py:43-52 does, one graph at a time), arg-max,
+    reprojection into the int16 (240,240,155) label volume.  value: graph, features and supervoxel map resident
+    in HBM; e2e: the same from pinned host buffers incl. the D2H copy of every label volume."""
+    from gnn_tumor_seg_b200 import graph as G, networks, ops, project, synth, _lib
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    _lib.load()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        if rank == 0:
+            for sd in range(N_DISTINCT_GRAPHS):
+                synth.make_graph(sd, with_partition=True)
+        dist.barrier()
+    ops.set_gemm_mode(args.mode)
+    peaks = load_peaks()
+    graphs = [synth.make_graph(sd, with_partition=True) for sd in range(N_DISTINCT_GRAPHS)]
+    my_ids = list(range(rank, args.infer_graphs, world))          # round-robin shard
+    torch.manual_seed(0)
+    net = networks.GraphSage(IN_FEATS, LAYER_SIZES, N_CLASSES, "pool", 0).to(dev).eval()
+    host = []
+    for g in graphs:
+        hg = G.from_edge_list(g.src, g.dst, g.n_nodes, pin=True)
+        host.append((hg, torch.as_tensor(g.features).pin_memory(), torch.as_tensor(g.svs).pin_memory(), g.crop))
+    resident = [(hg.to(dev), f.to(dev), s.to(dev), project.crop_inverse_maps(c, device=dev)) for hg, f, s, c in host]
+    vol = torch.empty(project.BRATS_SHAPE, dtype=torch.int16, device=dev)
+    vol_host = torch.empty(project.BRATS_SHAPE, dtype=torch.int16).pin_memory()
+
+    def one(i, e2e):
+        k = i % N_DISTINCT_GRAPHS
+        if e2e:
+            hg, f, s, c = host[k]
+            dg, fd, sd_ = hg.to(dev), f.to(dev, non_blocking=True), s.to(dev, non_blocking=True)
+            inv = resident[k][3]
+        else:
+            dg, fd, sd_, inv = resident[k]
+        with torch.no_grad():
+            logits = net(dg, fd)
+        project.project_labels_to_brats(logits, sd_, None, out=vol, inv_maps=inv)
+        if e2e:
+            vol_host.copy_(vol, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(e2e, steps):
+        for i in range(min(len(my_ids), 24)):
+            one(my_ids[i], e2e)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            for i in my_ids:
+                one(i, e2e)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / steps
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = ops.launch_counter["n"]
+    ms = timed(False, args.steps)
+    launches = ops.launch_counter["n"] - n0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(True, max(1, args.steps // 2))
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank == 0:
+        g0 = graphs[0]
+        # reprojection kernel alone, live: 2*X*Y*Z map read + 2*240*240*155 volume write + 4*N (SURVEY §8d)
+        cls = torch.zeros(g0.n_nodes, dtype=torch.int32, device=dev)
+        ms_proj = time_kernel(lambda i: project.project_labels_to_brats(cls, resident[i % N_DISTINCT_GRAPHS][2], None, out=vol,
+                                                                         inv_maps=resident[i % N_DISTINCT_GRAPHS][3]), 50)
+        proj_bytes = 2 * g0.svs.size + 2 * int(np.prod(project.BRATS_SHAPE)) + 4 * g0.n_nodes
+        gbs = proj_bytes / (ms_proj * 1e-3) / 1e9
+        h2d = g0.n_edges * 8 + g0.n_nodes * IN_FEATS * 4 + g0.svs.size * 2
+        line = {
+            "metric": "graphs_per_s", "value": args.infer_graphs / (ms * 1e-3), "unit": "graphs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3"}[args.mode], "data": "synthetic",
+            "edges_per_s": args.infer_graphs * g0.n_edges / (ms * 1e-3),
+            "config": {"workload": "bulk inference of %d synthetic 15k-node graphs (8 distinct, cycled) GraphSAGE-pool 7x256 eval forward "
+                                   "+ arg-max + node->voxel reprojection to int16 240x240x155, graphs round-robin over ranks "
+                                   "(BASELINE configs[4])" % args.infer_graphs,
+                       "gemm_mode": args.mode, "graphs_per_forward": 1, "parallelism": "dp%d (no collective)" % world,
+                       "l2_policy": "8 distinct graphs cycled: 8 x (15.4 MB activations x layers + 6.8 MB map + 17.9 MB volume) > L2"},
+            "clocks": clocks,
+            "e2e": {"value": args.infer_graphs / (ms_e2e * 1e-3), "unit": "graphs/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(h2d * len(my_ids)), "d2h_bytes_per_step": int(2 * np.prod(project.BRATS_SHAPE) * len(my_ids))},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "project_labels", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs / peaks["hbm_gbs"], "traffic": None, "ms": ms_proj, "alg_bytes": proj_bytes,
+                         "note": "reprojection kernel alone; the job is dominated by the per-graph forward (one 15k-node graph "
+                                 "fills 59 of 74 CTA-pair tiles per GEMM)"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -424,9 +570,15 @@ def main():
     ap.add_argument("--batch", type=int, default=6)
     ap.add_argument("--rotate", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="train", choices=["train", "infer"],
+                    help="train = BASELINE configs[1]/[3] (the headline); infer = configs[4] bulk inference + reprojection")
+    ap.add_argument("--infer-graphs", type=int, default=1251)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "infer":
+        args.steps = min(args.steps, 3)
+        run_infer(args)
     else:
         args.warmup = max(args.warmup, 3)
         run_ours(args)

@@ -158,6 +158,41 @@ __global__ void splitk_reduce_vec_kernel(const float4* __restrict__ partial, int
   }
 }
 
+// Wide variant: 128 threads = 32 consecutive float4 outputs x 4 split groups (warp g sums the splits z = g, g+4, ...,
+// all loads in flight), then warp 0 adds the four partial sums in a fixed order -> deterministic, 4x the parallelism
+// of one thread per output (a 256x256 weight gradient has only 16 384 float4 outputs).  Outputs [0, main4) go to C,
+// outputs [main4, total4) to `tail` (the fused column sums of the weight-gradient GEMM).
+__global__ void __launch_bounds__(128)
+splitk_reduce_wide_kernel(const float4* __restrict__ partial, int64_t split_stride4, int splits, int64_t main4,
+                          int64_t total4, float4* __restrict__ C, float4* __restrict__ tail) {
+  __shared__ float4 red[3][32];
+  const int o = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + o;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < total4) {
+    int z = g;
+    for (; z + 12 < splits; z += 16) {
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = ldg_nc_na(partial + (int64_t)(z + 4 * j) * split_stride4 + i);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; }
+    }
+    for (; z < splits; z += 4) {
+      const float4 v = ldg_nc_na(partial + (int64_t)z * split_stride4 + i);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  if (g > 0) red[g - 1][o] = s;
+  __syncthreads();
+  if (g == 0 && i < total4) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { const float4 v = red[j][o]; s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+    if (i < main4) C[i] = s;
+    else tail[i - main4] = s;
+  }
+}
+
 // Column sums, wide fast path (cols % 4 == 0, cols <= 1024, 16-byte aligned rows):
 // block = 256 threads = (cols/4 column groups) x (256/(cols/4) row lanes); float4 loads.
 __global__ void __launch_bounds__(256)
@@ -262,9 +297,29 @@ __global__ void transpose_kernel(const float* __restrict__ in, int64_t ldin, int
   }
 }
 
+// partial[z] = [rows*cols product | tail_len extra floats]; C contiguous; everything a multiple of 4 floats and
+// 16-byte aligned (the caller checks with splitk_reduce_fused_ok)
+bool splitk_reduce_fused_ok(int64_t rows, int64_t cols, int64_t ldc, int64_t tail_len, int64_t split_stride,
+                            const void* partial, const void* C, const void* tail) {
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  return ldc == cols && (rows * cols) % 4 == 0 && tail_len % 4 == 0 && split_stride % 4 == 0 && al(partial) && al(C) &&
+         (tail_len == 0 || al(tail));
+}
+void launch_splitk_reduce_fused(const float* partial, int64_t split_stride, int splits, int64_t rows, int64_t cols,
+                                float* C, float* tail, int64_t tail_len, cudaStream_t st) {
+  const int64_t main4 = rows * cols / 4, total4 = main4 + tail_len / 4;
+  const int blocks = (int)ceil_div<int64_t>(total4, 32);
+  splitk_reduce_wide_kernel<<<blocks, 128, 0, st>>>(reinterpret_cast<const float4*>(partial), split_stride / 4, splits, main4,
+                                                    total4, reinterpret_cast<float4*>(C), reinterpret_cast<float4*>(tail));
+}
+
 void launch_splitk_reduce(const float* partial, int64_t split_stride, int splits, int64_t rows, int64_t cols,
                           float* C, int64_t ldc, cudaStream_t st) {
   const int64_t total = rows * cols;
+  if (splits >= 8 && splitk_reduce_fused_ok(rows, cols, ldc, 0, split_stride, partial, C, nullptr)) {
+    launch_splitk_reduce_fused(partial, split_stride, splits, rows, cols, C, nullptr, 0, st);
+    return;
+  }
   const bool vec = ldc == cols && total % 4 == 0 && split_stride % 4 == 0 &&
                    (reinterpret_cast<uintptr_t>(partial) & 15u) == 0 && (reinterpret_cast<uintptr_t>(C) & 15u) == 0;
   if (vec) {

@@ -31,6 +31,10 @@ namespace gts {
 
 void launch_splitk_reduce(const float* partial, int64_t split_stride, int splits, int64_t rows, int64_t cols,
                           float* C, int64_t ldc, cudaStream_t st);   // gemm_simt.cu
+bool splitk_reduce_fused_ok(int64_t rows, int64_t cols, int64_t ldc, int64_t tail_len, int64_t split_stride,
+                            const void* partial, const void* C, const void* tail);
+void launch_splitk_reduce_fused(const float* partial, int64_t split_stride, int splits, int64_t rows, int64_t cols,
+                                float* C, float* tail, int64_t tail_len, cudaStream_t st);
 
 namespace tc {
 
@@ -697,7 +701,7 @@ gemm_x3ts_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       if (TN && p.colsum_partial) {
         const int split = w % p.splits, tile = w / p.splits;
         const int m = (tile / p.tiles_n) * BM + r;
-        if (tile % p.tiles_n == 0 && m < p.M) p.colsum_partial[(int64_t)split * p.M + m] = csum;
+        if (tile % p.tiles_n == 0 && m < p.M) p.colsum_partial[(int64_t)split * p.split_stride + m] = csum;
       }
     }
   } else if (warp < 10) {
@@ -1060,7 +1064,7 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       if (TN && p.colsum_partial) {
         const int split = w % p.splits, tile = w / p.splits;
         const int m = (tile / p.tiles_n) * (2 * BM) + (int)rank * BM + r;
-        if (tile % p.tiles_n == 0 && m < p.M) p.colsum_partial[(int64_t)split * p.M + m] = csum;
+        if (tile % p.tiles_n == 0 && m < p.M) p.colsum_partial[(int64_t)split * p.split_stride + m] = csum;
       }
     }
   } else if (warp < 10) {
@@ -1323,13 +1327,14 @@ static void tn_plan(int32_t Mo, int32_t No, int64_t K, int32_t mode, tc::Params&
   p.split_stride = (int64_t)Mo * No;
 }
 
-// workspace: [splits][Mo][No] partial products, then [splits][Mo] partial column sums of A
+// workspace: per split one record [Mo*No partial product | Mo (rounded up to 4) partial column sums of A]
+static inline int64_t tn_record(int32_t Mo, int32_t No) { return (int64_t)Mo * No + (((int64_t)Mo + 3) / 4) * 4; }
+
 size_t gemm_tn_tcgen05_ws(int32_t Mo, int32_t No, int64_t K, int32_t mode) {
   if (Mo < 1 || No < 1 || K < 1) return 0;
   tc::Params p{};
   tn_plan(Mo, No, K, mode, p);
-  return align_up((size_t)p.splits * (size_t)Mo * (size_t)No * sizeof(float), 256) +
-         align_up((size_t)p.splits * (size_t)Mo * sizeof(float), 256);
+  return align_up((size_t)p.splits * (size_t)tn_record(Mo, No) * sizeof(float), 256);
 }
 
 // true when gemm_tn_tcgen05 can produce the column sums of A as a by-product (3xTF32, A staged through TMEM)
@@ -1342,14 +1347,15 @@ int gemm_tn_tcgen05(const float* A, int64_t lda, const float* B, int64_t ldb, fl
   const bool x3 = mode == GTS_GEMM_TF32X3;
   Params p{};
   tn_plan(Mo, No, K, mode, p);
-  const size_t prod_bytes = align_up((size_t)p.splits * (size_t)Mo * (size_t)No * sizeof(float), 256);
-  const size_t need = prod_bytes + align_up((size_t)p.splits * (size_t)Mo * sizeof(float), 256);
+  const int64_t record = tn_record(Mo, No);
+  const size_t need = align_up((size_t)p.splits * (size_t)record * sizeof(float), 256);
   if (!ws || ws_bytes < need) { set_error("gts_gemm_tn: workspace %zu < required %zu", ws_bytes, need); return GTS_ERR_WORKSPACE; }
   p.M = Mo; p.N = No;
   p.C = reinterpret_cast<float*>(ws); p.ldc = No;
+  p.split_stride = record;
   const bool in_tmem = x3 && x3_in_tmem();
   if (colsum_out && !in_tmem) { set_error("gts_gemm_tn: fused column sums need the 3xTF32 A-in-TMEM kernel"); return GTS_ERR_INVALID; }
-  float* cs_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + prod_bytes);
+  float* cs_partial = p.C + (int64_t)Mo * No;
   p.colsum_partial = colsum_out ? cs_partial : nullptr;
   CUtensorMap tA, tB;
   if (!encode_2d(&tA, A, K, Mo, lda, 32, BK, !x3, true)) return GTS_ERR_CUDA;
@@ -1361,10 +1367,17 @@ int gemm_tn_tcgen05(const float* A, int64_t lda, const float* B, int64_t ldb, fl
                                          : launch_ts<true, 128>(tA, tA, tB, tB, p, n_work, st))
                    : (x3 ? launch<true, true>(tA, tA, tB, tB, p, n_work, st) : launch<true, false>(tA, tA, tB, tB, p, n_work, st));
   if (rc != GTS_OK) return rc;
-  launch_splitk_reduce(p.C, p.split_stride, p.splits, Mo, No, C, ldc, st);
+  // one deterministic reduction over the splits for the product and (when fused) the column sums
+  if (colsum_out && Mo % 4 == 0 && p.splits >= 8 &&
+      splitk_reduce_fused_ok(Mo, No, ldc, Mo, record, p.C, C, colsum_out)) {
+    launch_splitk_reduce_fused(p.C, record, p.splits, Mo, No, C, colsum_out, Mo, st);
+    GTS_LAUNCH_CHECK();
+    return GTS_OK;
+  }
+  launch_splitk_reduce(p.C, record, p.splits, Mo, No, C, ldc, st);
   GTS_LAUNCH_CHECK();
   if (colsum_out) {
-    launch_splitk_reduce(cs_partial, Mo, p.splits, 1, Mo, colsum_out, Mo, st);
+    launch_splitk_reduce(cs_partial, record, p.splits, 1, Mo, colsum_out, Mo, st);
     GTS_LAUNCH_CHECK();
   }
   return GTS_OK;

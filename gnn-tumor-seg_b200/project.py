@@ -24,6 +24,19 @@ def _device():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+_LUT_CACHE = {}
+
+
+def _lut_on(device, label_lut):
+    """The relabelling table as a cached int16 device tensor (one H2D copy per device and table, not per call)."""
+    key = (str(device), tuple(int(v) for v in label_lut))
+    t = _LUT_CACHE.get(key)
+    if t is None:
+        t = torch.as_tensor(np.asarray(label_lut, dtype=np.int16)).to(device)
+        _LUT_CACHE[key] = t
+    return t
+
+
 def _as_dev(x, dtype, device):
     if torch.is_tensor(x):
         return x.to(device=device, dtype=dtype, non_blocking=True).contiguous()
@@ -97,7 +110,7 @@ def project_labels_to_brats(node_logits_or_classes, svs, crop, full_shape=BRATS_
         X, Y, Z = svs_d.shape
         if inv_maps is None:
             inv_maps = crop_inverse_maps(crop, full_shape, dev)
-        lut = torch.as_tensor(np.asarray(label_lut, dtype=np.int16)).to(dev, non_blocking=True)
+        lut = _lut_on(dev, label_lut)
         if out is None:
             out = torch.empty(full_shape, dtype=torch.int16, device=dev)
         err = torch.zeros(1, dtype=torch.int32, device=dev)
