@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgts.so")
 
 GTS_OK = 0
-ACT_NONE, ACT_RELU, ACT_MASK_POS = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_MASK_POS, ACT_MASK_POS_SCATTER = 0, 1, 2, 3
 GEMM_FP32, GEMM_TF32, GEMM_TF32X3 = 0, 1, 2
 GEMM_MODES = {"fp32": GEMM_FP32, "tf32": GEMM_TF32, "tf32x3": GEMM_TF32X3}
 
@@ -38,6 +38,8 @@ class GemmNtArgs(C.Structure):
         ("M", C.c_int32), ("N", C.c_int32),
         ("act", C.c_int32), ("mode", C.c_int32),
         ("bias2", C.c_void_p),
+        ("scatter_idx", C.c_void_p), ("ld_idx", C.c_int64),
+        ("scatter_out", C.c_void_p), ("ld_out", C.c_int64),
     ]
 
 

@@ -34,6 +34,15 @@ inline cudaStream_t as_stream(gts_stream_t s) { return reinterpret_cast<cudaStre
 
 int sm_count();   // cached SM count of the current device
 
+// out[c, r] = in[r, c] for up to kMaxJobs small matrices in one launch (gemm_simt.cu)
+struct TransposeJob { const float* in; float* out; int64_t ldin, ldout; int32_t rows, cols; };
+struct TransposeBatch {
+  static constexpr int kMaxJobs = 96;
+  int n = 0;
+  TransposeJob job[kMaxJobs];
+};
+int launch_transpose_batch(const TransposeBatch& b, cudaStream_t st);
+
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
 

@@ -57,7 +57,9 @@ __global__ void __launch_bounds__(kSimtThreads)
 gemm_simt_kernel(Operand A1, Operand B1, int64_t K1, Operand A2, Operand B2, int64_t K2,
                  int64_t M, int64_t N, float* __restrict__ C, int64_t ldc,
                  const float* __restrict__ bias, const float* __restrict__ bias2, const float* __restrict__ aux, int64_t ldaux, int act,
-                 int64_t k_per_split, int64_t split_stride) {
+                 int64_t k_per_split, int64_t split_stride,
+                 const int32_t* __restrict__ sidx = nullptr, int64_t ld_sidx = 0, float* __restrict__ sout = nullptr,
+                 int64_t ld_sout = 0) {
   static_assert((BM / TM) * (BN / TN) == kSimtThreads, "thread tiling must cover the block tile");
   __shared__ float As[kBK][BM + 4];
   __shared__ float Bs[kBK][BN + 4];
@@ -118,7 +120,12 @@ gemm_simt_kernel(Operand A1, Operand B1, int64_t K1, Operand A2, Operand B2, int
         if (bias) v += bias[n];
         if (bias2) v += bias2[n];
         if (act == GTS_ACT_RELU) v = fmaxf(v, 0.f);
-        else if (act == GTS_ACT_MASK_POS) v = (aux[m * ldaux + n] > 0.f) ? v : 0.f;
+        else if (act == GTS_ACT_MASK_POS || act == GTS_ACT_MASK_POS_SCATTER) v = (aux[m * ldaux + n] > 0.f) ? v : 0.f;
+        if (act == GTS_ACT_MASK_POS_SCATTER) {
+          const int32_t u = sidx[m * ld_sidx + n];
+          if (u >= 0 && v != 0.f) atomicAdd(sout + (int64_t)u * ld_sout + n, v);
+          continue;
+        }
       }
       Cout[m * ldc + n] = v;
     }
@@ -313,6 +320,35 @@ void launch_splitk_reduce_fused(const float* partial, int64_t split_stride, int 
                                                     total4, reinterpret_cast<float4*>(C), reinterpret_cast<float4*>(tail));
 }
 
+// All weight transposes of one backward pass in ONE launch: blockIdx.z picks the matrix.
+__global__ void transpose_batch_kernel(const TransposeBatch b) {
+  const TransposeJob j = b.job[blockIdx.z];
+  if ((int)blockIdx.x * 32 >= j.cols || (int)blockIdx.y * 32 >= j.rows) return;
+  __shared__ float t[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = blockIdx.y * 32 + i;
+    if (r < j.rows && c < j.cols) t[i][threadIdx.x] = j.in[(int64_t)r * j.ldin + c];
+  }
+  __syncthreads();
+  const int r2 = blockIdx.y * 32 + threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c2 = blockIdx.x * 32 + i;
+    if (c2 < j.cols && r2 < j.rows) j.out[(int64_t)c2 * j.ldout + r2] = t[threadIdx.x][i];
+  }
+}
+
+int launch_transpose_batch(const TransposeBatch& b, cudaStream_t st) {
+  if (b.n <= 0) return GTS_OK;
+  int max_r = 0, max_c = 0;
+  for (int i = 0; i < b.n; ++i) { max_r = b.job[i].rows > max_r ? b.job[i].rows : max_r; max_c = b.job[i].cols > max_c ? b.job[i].cols : max_c; }
+  if (max_r == 0 || max_c == 0) return GTS_OK;
+  dim3 grid((max_c + 31) / 32, (max_r + 31) / 32, b.n), block(32, 8);
+  transpose_batch_kernel<<<grid, block, 0, st>>>(b);
+  GTS_LAUNCH_CHECK();
+  return GTS_OK;
+}
+
 void launch_splitk_reduce(const float* partial, int64_t split_stride, int splits, int64_t rows, int64_t cols,
                           float* C, int64_t ldc, cudaStream_t st) {
   const int64_t total = rows * cols;
@@ -364,11 +400,13 @@ static int gemm_nt_simt(const gts_gemm_nt_args* a, cudaStream_t st) {
   if (a->N <= 16) {
     dim3 grid((unsigned)ceil_div<int64_t>(a->N, 16), (unsigned)ceil_div<int64_t>(a->M, 128));
     gemm_simt_kernel<128, 16, 8, 1, true, true, false><<<grid, kSimtThreads, 0, st>>>(
-        A1, B1, a->K1, A2, B2, K2, a->M, a->N, a->C, a->ldc, a->bias, a->bias2, a->aux, a->ldaux, a->act, 0, 0);
+        A1, B1, a->K1, A2, B2, K2, a->M, a->N, a->C, a->ldc, a->bias, a->bias2, a->aux, a->ldaux, a->act, 0, 0,
+        a->scatter_idx, a->ld_idx, a->scatter_out, a->ld_out);
   } else {
     dim3 grid((unsigned)ceil_div<int64_t>(a->N, 128), (unsigned)ceil_div<int64_t>(a->M, 128));
     gemm_simt_kernel<128, 128, 8, 8, true, true, false><<<grid, kSimtThreads, 0, st>>>(
-        A1, B1, a->K1, A2, B2, K2, a->M, a->N, a->C, a->ldc, a->bias, a->bias2, a->aux, a->ldaux, a->act, 0, 0);
+        A1, B1, a->K1, A2, B2, K2, a->M, a->N, a->C, a->ldc, a->bias, a->bias2, a->aux, a->ldaux, a->act, 0, 0,
+        a->scatter_idx, a->ld_idx, a->scatter_out, a->ld_out);
   }
   GTS_LAUNCH_CHECK();
   return GTS_OK;
@@ -415,9 +453,11 @@ int gts_gemm_nt(const gts_gemm_nt_args* a, gts_stream_t stream) {
   GTS_CHECK_ARG(a != nullptr, "gts_gemm_nt: args is null");
   GTS_CHECK_ARG(a->M >= 0 && a->N >= 0 && a->K1 >= 0 && a->K2 >= 0, "gts_gemm_nt: negative size");
   if (a->M == 0 || a->N == 0) return GTS_OK;
-  GTS_CHECK_ARG(a->C != nullptr, "gts_gemm_nt: C is null");
+  GTS_CHECK_ARG(a->C != nullptr || a->act == GTS_ACT_MASK_POS_SCATTER, "gts_gemm_nt: C is null");
+  GTS_CHECK_ARG(a->act != GTS_ACT_MASK_POS_SCATTER || (a->scatter_idx && a->scatter_out && a->aux),
+                "gts_gemm_nt: GTS_ACT_MASK_POS_SCATTER needs aux, scatter_idx and scatter_out");
   GTS_CHECK_ARG(a->K1 == 0 || (a->A1 && a->B1), "gts_gemm_nt: A1/B1 null with K1 > 0");
-  GTS_CHECK_ARG(a->act >= GTS_ACT_NONE && a->act <= GTS_ACT_MASK_POS, "gts_gemm_nt: unknown act %d", a->act);
+  GTS_CHECK_ARG(a->act >= GTS_ACT_NONE && a->act <= GTS_ACT_MASK_POS_SCATTER, "gts_gemm_nt: unknown act %d", a->act);
   GTS_CHECK_ARG(a->act != GTS_ACT_MASK_POS || a->aux != nullptr, "gts_gemm_nt: GTS_ACT_MASK_POS needs aux");
   cudaStream_t st = as_stream(stream);
   if (a->mode == GTS_GEMM_FP32) return gemm_nt_simt(a, st);

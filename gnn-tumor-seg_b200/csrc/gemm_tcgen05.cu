@@ -1262,6 +1262,7 @@ bool gemm_nt_tcgen05_supported(const gts_gemm_nt_args* a) {
   if (a->K1 < 1 || !tc::operand_ok(a->A1, a->lda1) || !tc::operand_ok(a->B1, a->ldb1)) return false;
   const bool two = a->A2 && a->B2 && a->K2 > 0;
   if (two && (!tc::operand_ok(a->A2, a->lda2) || !tc::operand_ok(a->B2, a->ldb2))) return false;
+  if (a->act == GTS_ACT_MASK_POS_SCATTER) return false;     // scatter epilogue: SIMT kernel only (measured slower when fused into the tcgen05 epilogue)
   if (!tc::al16(a->C) || a->ldc % 4 != 0) return false;
   if (a->bias && !tc::al16(a->bias)) return false;
   if (a->bias2 && !tc::al16(a->bias2)) return false;

@@ -11,7 +11,8 @@ struct StackPlan {
   int L = 0;
   int64_t N = 0;
   size_t neigh[kMaxLayers], arg[kMaxLayers], out[kMaxLayers];
-  size_t P = 0, g0 = 0, g1 = 0, dP = 0, wt0 = 0, wt1 = 0, gemm_ws = 0, colsum_ws = 0;
+  size_t P = 0, g0 = 0, g1 = 0, dP = 0, gemm_ws = 0, colsum_ws = 0;
+  size_t wnT[kMaxLayers], wsT[kMaxLayers], wpT[kMaxLayers];      // transposed weights of every layer (one batched launch)
   size_t gemm_ws_bytes = 0, colsum_ws_bytes = 0;
   size_t total = 0;
 };
@@ -22,15 +23,12 @@ static bool make_plan(const gts_sage_layer* layers, int L, int64_t N, bool train
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes ? bytes : 16, 256); return o; };
   int max_din = 0, max_dim = 0;
-  size_t max_w = 0;
   for (int l = 0; l < L; ++l) {
     if (layers[l].din < 1 || layers[l].dout < 1) return false;
     if (l > 0 && layers[l].din != layers[l - 1].dout) return false;
     max_din = layers[l].din > max_din ? layers[l].din : max_din;
     max_dim = layers[l].din > max_dim ? layers[l].din : max_dim;
     max_dim = layers[l].dout > max_dim ? layers[l].dout : max_dim;
-    size_t w = (size_t)layers[l].din * (size_t)(layers[l].dout > layers[l].din ? layers[l].dout : layers[l].din);
-    max_w = w > max_w ? w : max_w;
   }
   const size_t n = (size_t)N;
   if (training) {
@@ -43,8 +41,11 @@ static bool make_plan(const gts_sage_layer* layers, int L, int64_t N, bool train
     pl.g0 = take(n * max_dim * 4);       // backward: dZ / dh ping-pong
     pl.g1 = take(n * max_dim * 4);
     pl.dP = take(n * max_din * 4);
-    pl.wt0 = take(max_w * 4);
-    pl.wt1 = take(max_w * 4);
+    for (int l = 0; l < L; ++l) {
+      pl.wnT[l] = take((size_t)layers[l].din * layers[l].dout * 4);
+      pl.wsT[l] = take((size_t)layers[l].din * layers[l].dout * 4);
+      pl.wpT[l] = take((size_t)layers[l].din * layers[l].din * 4);
+    }
     size_t gw = 256, cw = 256;
     for (int l = 0; l < L; ++l) {
       size_t a = gts_gemm_tn_colsum_workspace_bytes(layers[l].dout, layers[l].din, N, mode);
@@ -78,6 +79,7 @@ static int nt(const float* A1, int64_t lda1, int K1, const float* B1, int64_t ld
               const float* B2, int64_t ldb2, const float* bias, int act, const float* aux, int64_t ldaux, float* C,
               int64_t ldc, int M, int N, int mode, gts_stream_t st, const float* bias2 = nullptr) {
   gts_gemm_nt_args a;
+  a.scatter_idx = nullptr; a.ld_idx = 0; a.scatter_out = nullptr; a.ld_out = 0;
   a.bias2 = bias2;
   a.A1 = A1; a.lda1 = lda1; a.K1 = K1; a.A2 = A2; a.lda2 = lda2; a.K2 = K2;
   a.B1 = B1; a.ldb1 = ldb1; a.B2 = B2; a.ldb2 = ldb2; a.bias = bias; a.aux = aux; a.ldaux = ldaux;
@@ -156,6 +158,25 @@ int gts_sage_backward(const gts_sage_layer* layers, const gts_sage_layer_grads* 
   const float* dZ = dlogits;
   int64_t ldz = ldd;
   int pp = 0;
+  // every weight transpose of the pass (data-gradient GEMMs consume K-major B operands) in launches of <= 96 jobs
+  {
+    TransposeBatch tb;
+    auto push = [&](const float* in, int rows, int cols, size_t off) -> int {
+      if (tb.n == TransposeBatch::kMaxJobs) { int rc = launch_transpose_batch(tb, as_stream(stream)); if (rc != GTS_OK) return rc; tb.n = 0; }
+      tb.job[tb.n++] = TransposeJob{in, at(workspace, off), cols, rows, rows, cols};
+      return GTS_OK;
+    };
+    for (int l = 0; l < n_layers && N > 0; ++l) {
+      const gts_sage_layer& ly = layers[l];
+      GTS_CHECK_ARG(ly.Wp && ly.Ws && ly.Wn, "gts_sage_backward: layer %d has a null weight", l);
+      GTS_TRY(push(ly.Wn, ly.dout, ly.din, pl.wnT[l]));
+      if (l > 0 || dfeats) {
+        GTS_TRY(push(ly.Ws, ly.dout, ly.din, pl.wsT[l]));
+        GTS_TRY(push(ly.Wp, ly.din, ly.din, pl.wpT[l]));
+      }
+    }
+    GTS_TRY(launch_transpose_batch(tb, as_stream(stream)));
+  }
   for (int l = n_layers - 1; l >= 0; --l) {
     const gts_sage_layer& ly = layers[l];
     const gts_sage_layer_grads& g = grads[l];
@@ -170,8 +191,10 @@ int gts_sage_backward(const gts_sage_layer* layers, const gts_sage_layer_grads* 
     GTS_TRY(gts_gemm_tn_colsum(dZ, ldz, h, ldh, g.dWs, ly.din, ly.dout, ly.din, N, mode, g.db, gws, pl.gemm_ws_bytes, stream));
     GTS_TRY(gts_gemm_tn(dZ, ldz, neigh, ly.din, g.dWn, ly.din, ly.dout, ly.din, N, mode, gws, pl.gemm_ws_bytes, stream));
     // dNeigh' = (dZ Wn) * (neigh > 0)
-    float* WnT = at(workspace, pl.wt0);
-    GTS_TRY(gts_transpose(ly.Wn, ly.din, ly.dout, ly.din, WnT, ly.dout, stream));
+    const float* WnT = at(workspace, pl.wnT[l]);
+    // Measured (profiles/r01_gemm_x3_pipeline.md): routing the masked tile through the arg-max from inside the GEMM
+    // epilogue (GTS_ACT_MASK_POS_SCATTER) is correct but slower — 320 us against 60 (GEMM) + 118 (zero-fill + scatter):
+    // four epilogue warps per SM cannot keep as many REDs in flight as a full-occupancy scatter kernel.
     float* dNeigh = at(workspace, pl.P);
     GTS_TRY(nt(dZ, ldz, ly.dout, WnT, ly.dout, nullptr, 0, 0, nullptr, 0, nullptr, GTS_ACT_MASK_POS, neigh, ly.din, dNeigh,
                ly.din, N, ly.din, mode, stream));
@@ -182,10 +205,8 @@ int gts_sage_backward(const gts_sage_layer* layers, const gts_sage_layer_grads* 
       GTS_TRY(gts_segmax_bwd(dNeigh, ly.din, arg, ly.din, N, ly.din, dP, ly.din, N, stream));
     GTS_TRY(gts_gemm_tn_colsum(dP, ly.din, h, ldh, g.dWp, ly.din, ly.din, ly.din, N, mode, g.dbp, gws, pl.gemm_ws_bytes, stream));
     if (l > 0 || dfeats) {
-      float* WsT = at(workspace, pl.wt0);
-      float* WpT = at(workspace, pl.wt1);
-      GTS_TRY(gts_transpose(ly.Ws, ly.din, ly.dout, ly.din, WsT, ly.dout, stream));
-      GTS_TRY(gts_transpose(ly.Wp, ly.din, ly.din, ly.din, WpT, ly.din, stream));
+      const float* WsT = at(workspace, pl.wsT[l]);
+      const float* WpT = at(workspace, pl.wpT[l]);
       float* dh;
       int64_t lddh;
       if (l == 0) { dh = dfeats; lddh = lddf; }

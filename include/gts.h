@@ -48,7 +48,12 @@ enum gts_status {
 enum gts_act {
   GTS_ACT_NONE = 0,
   GTS_ACT_RELU = 1,     /* C = max(acc + bias, 0) */
-  GTS_ACT_MASK_POS = 2  /* C = (aux > 0) ? acc + bias : 0   (ReLU backward mask) */
+  GTS_ACT_MASK_POS = 2, /* C = (aux > 0) ? acc + bias : 0   (ReLU backward mask) */
+  GTS_ACT_MASK_POS_SCATTER = 3  /* v = (aux > 0) ? acc : 0 is NOT stored to C: it is routed through saved arg-max indices,
+                                 * scatter_out[scatter_idx[m,n], n] += v (fp32 RED; rows with idx < 0 and v == 0 skipped).
+                                 * The backward of the neighbour max fused into the GEMM that produces its input:
+                                 * dP[argU[v,k],k] += ((dZ Wn) * (neigh > 0))[v,k]  (SURVEY.md Appendix A.1).
+                                 * scatter_out must be zero-filled by the caller; C may be NULL. */
 };
 
 /* GEMM arithmetic */
@@ -113,6 +118,8 @@ typedef struct gts_gemm_nt_args {
   int32_t act;   /* gts_act */
   int32_t mode;  /* gts_gemm_mode */
   const float* bias2;   /* optional second bias vector, added to bias (DGL<=0.7 keeps fc_self.bias and fc_neigh.bias) */
+  const int32_t* scatter_idx; int64_t ld_idx;   /* GTS_ACT_MASK_POS_SCATTER: arg-max indices [M,N] */
+  float* scatter_out; int64_t ld_out;           /* GTS_ACT_MASK_POS_SCATTER: destination [rows,N], zero-filled */
 } gts_gemm_nt_args;
 
 GTS_API int gts_gemm_nt(const gts_gemm_nt_args* args, gts_stream_t stream);

@@ -72,6 +72,26 @@ def test_gemm_tn_colsum_integer_exact(cuda_dev):
         assert torch.equal(cs.cpu(), A.sum(0))
 
 
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3", "tf32"])
+@pytest.mark.parametrize("M,N,K,R", [(90000, 256, 256, 90000), (5000, 256, 256, 777), (1000, 20, 256, 1000), (300, 4, 256, 300)])
+def test_gemm_nt_scatter(cuda_dev, mode, M, N, K, R):
+    """GTS_ACT_MASK_POS_SCATTER == masked GEMM followed by the arg-max scatter (segmax_bwd), also vs the fp64 oracle."""
+    g = torch.Generator().manual_seed(M + N)
+    A = torch.randn(M, K, generator=g); B = torch.randn(N, K, generator=g)
+    aux = torch.randn(M, N, generator=g)
+    idx = torch.randint(-1, R, (M, N), generator=g, dtype=torch.int64).to(torch.int32)
+    ref = torch.zeros(R, N, dtype=torch.float64)
+    v = (A.double() @ B.double().T) * (aux > 0)
+    ok = idx >= 0
+    cols = torch.arange(N).expand(M, N)
+    ref.index_put_((idx[ok].long(), cols[ok]), v[ok], accumulate=True)
+    dv = lambda t: t.to(cuda_dev)
+    out = ops.gemm_nt_scatter(dv(A), dv(B), dv(aux), dv(idx), R, mode=mode)
+    assert _rel(out.cpu(), ref) < TOL[mode]
+    two = ops.segmax_bwd(ops.gemm_nt(dv(A), dv(B), act=ACT_MASK_POS, aux=dv(aux), mode=mode), dv(idx), R)
+    assert _rel(out.cpu(), two.cpu().double()) < max(1e-5, TOL[mode])      # the fused mode always runs the exact fp32 kernel
+
+
 def test_gemm_strided_operands(cuda_dev):
     big = torch.randn(300, 512)
     A = big[:, 128:384]                       # ld 512
