@@ -118,6 +118,8 @@ _SIGNATURES = {
     "gts_gat_attn_grad_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "gts_gat_attn_grad": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int32, C.c_int32, C.c_int32, c_f32p,
                                     C.c_void_p, C.c_size_t, c_stream]),
+    "gts_gat_attn_grad2": (C.c_int, [c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, c_f32p, c_f32p,
+                                     C.c_void_p, C.c_size_t, c_stream]),
     "gts_adamw_step": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_float, C.c_float, C.c_float,
                                  C.c_float, C.c_float, C.c_int32, C.c_float, c_f32p, c_stream]),
 }

@@ -11,10 +11,13 @@
 // materialised; the only per-edge array is dt[E,H] in the backward.
 // HBM-bound: algorithmic bytes per layer 4*(2*N*H*F + 6*N*H) + 4*(N+1+E).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace gts {
 
 constexpr int kGatThreads = 256;
+// (A contiguous-(node, head)-range-per-SM distribution of the edge kernels, which pays off for the seg-max kernel, was
+// measured SLOWER here: 550 -> 678 us forward at 4 x 256 — only 8 nodes are in flight per SM, too few for L1 reuse.)
 constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ float warp_max(float x) {
@@ -105,19 +108,28 @@ __global__ void gat_scores_kernel(const float* __restrict__ Z, int64_t ldz, cons
   }
 }
 
-template <int VEC, bool VECTOR>
-__global__ void __launch_bounds__(kGatThreads)
+template <int VEC, bool VECTOR, bool RANGE>
+__global__ void __launch_bounds__(RANGE ? 1024 : kGatThreads, 1)
 gat_fwd_kernel(const float* __restrict__ Z, int64_t ldz, const float* __restrict__ el, const float* __restrict__ er,
                const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, int64_t NH, int H, int F,
                float slope, const float* __restrict__ res, int64_t ldres, const float* __restrict__ bias, int act,
                float* __restrict__ out, int64_t ldo, float* __restrict__ rowmax, float* __restrict__ rowsum,
                int32_t* __restrict__ err) {
   const int lane = threadIdx.x & 31;
-  const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t w = w0; w < NH; w += nw) {
-    const int64_t v = w / H;
-    const int h = (int)(w - v * H);
+  // RANGE: one 1024-thread CTA per SM owns a contiguous node range and walks it HEAD-MAJOR (all 32 warps on the same
+  // head of 32 consecutive nodes): consecutive supervoxels share most of their neighbours, so the 1 KB head slices of
+  // the neighbour rows are re-read from L1 (node-major order keeps 8 nodes x 4 heads x 15 rows in flight and thrashes it)
+  const int64_t n_total = NH / H;
+  const int64_t per_cta = RANGE ? (n_total + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t r_beg = RANGE ? (int64_t)blockIdx.x * per_cta : 0;
+  const int64_t r_cnt = RANGE ? max((int64_t)0, min(n_total, r_beg + per_cta) - r_beg) : 0;
+  const int64_t i_beg = RANGE ? (int64_t)(threadIdx.x >> 5) : ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  const int64_t i_end = RANGE ? r_cnt * H : NH;
+  const int64_t i_step = RANGE ? (int64_t)(blockDim.x >> 5) : (((int64_t)gridDim.x * blockDim.x) >> 5);
+  for (int64_t i = i_beg; i < i_end; i += i_step) {
+    const int h = RANGE ? (int)(i / r_cnt) : (int)(i % H);
+    const int64_t v = RANGE ? r_beg + (i - (int64_t)h * r_cnt) : i / H;
+    const int64_t w = v * H + h;
     const int32_t beg = indptr[v], end = indptr[v + 1];
     const float erv = er[w];
     // pass A: softmax statistics over the row's edges (one edge per lane)
@@ -187,19 +199,28 @@ __global__ void gat_act_bwd_kernel(const float* __restrict__ dout, const float* 
 }
 
 // Backward pass A, by destination.
-template <int VEC, bool VECTOR>
-__global__ void __launch_bounds__(kGatThreads)
+template <int VEC, bool VECTOR, bool RANGE>
+__global__ void __launch_bounds__(RANGE ? 1024 : kGatThreads, 1)
 gat_bwd_dst_kernel(const float* __restrict__ Z, int64_t ldz, const float* __restrict__ el, const float* __restrict__ er,
                    const float* __restrict__ rowmax, const float* __restrict__ rowsum,
                    const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                    const float* __restrict__ dO, int64_t lddo, int64_t NH, int H, int F, float slope,
                    float* __restrict__ dt_edge, float* __restrict__ der) {
   const int lane = threadIdx.x & 31;
-  const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t w = w0; w < NH; w += nw) {
-    const int64_t v = w / H;
-    const int h = (int)(w - v * H);
+  // RANGE: one 1024-thread CTA per SM owns a contiguous node range and walks it HEAD-MAJOR (all 32 warps on the same
+  // head of 32 consecutive nodes): consecutive supervoxels share most of their neighbours, so the 1 KB head slices of
+  // the neighbour rows are re-read from L1 (node-major order keeps 8 nodes x 4 heads x 15 rows in flight and thrashes it)
+  const int64_t n_total = NH / H;
+  const int64_t per_cta = RANGE ? (n_total + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t r_beg = RANGE ? (int64_t)blockIdx.x * per_cta : 0;
+  const int64_t r_cnt = RANGE ? max((int64_t)0, min(n_total, r_beg + per_cta) - r_beg) : 0;
+  const int64_t i_beg = RANGE ? (int64_t)(threadIdx.x >> 5) : ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  const int64_t i_end = RANGE ? r_cnt * H : NH;
+  const int64_t i_step = RANGE ? (int64_t)(blockDim.x >> 5) : (((int64_t)gridDim.x * blockDim.x) >> 5);
+  for (int64_t i = i_beg; i < i_end; i += i_step) {
+    const int h = RANGE ? (int)(i / r_cnt) : (int)(i % H);
+    const int64_t v = RANGE ? r_beg + (i - (int64_t)h * r_cnt) : i / H;
+    const int64_t w = v * H + h;
     const int32_t beg = indptr[v], end = indptr[v + 1];
     const float erv = er[w], m = rowmax[w];
     const float inv_l = end > beg ? 1.f / rowsum[w] : 0.f;
@@ -246,8 +267,8 @@ gat_bwd_dst_kernel(const float* __restrict__ Z, int64_t ldz, const float* __rest
 }
 
 // Backward pass B, by source over the out-edge CSC.
-template <int VEC, bool VECTOR>
-__global__ void __launch_bounds__(kGatThreads)
+template <int VEC, bool VECTOR, bool RANGE>
+__global__ void __launch_bounds__(RANGE ? 1024 : kGatThreads, 1)
 gat_bwd_src_kernel(const float* __restrict__ el, const float* __restrict__ er, const float* __restrict__ rowmax,
                    const float* __restrict__ rowsum, const int32_t* __restrict__ cptr, const int32_t* __restrict__ cidx,
                    const int32_t* __restrict__ csc2csr, const float* __restrict__ dO, int64_t lddo,
@@ -255,11 +276,20 @@ gat_bwd_src_kernel(const float* __restrict__ el, const float* __restrict__ er, c
                    const float* __restrict__ ar, int64_t NH, int H, int F, float slope,
                    float* __restrict__ dZ, int64_t lddz, float* __restrict__ del) {
   const int lane = threadIdx.x & 31;
-  const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t w = w0; w < NH; w += nw) {
-    const int64_t u = w / H;
-    const int h = (int)(w - u * H);
+  // RANGE: one 1024-thread CTA per SM owns a contiguous node range and walks it HEAD-MAJOR (all 32 warps on the same
+  // head of 32 consecutive nodes): consecutive supervoxels share most of their neighbours, so the 1 KB head slices of
+  // the neighbour rows are re-read from L1 (node-major order keeps 8 nodes x 4 heads x 15 rows in flight and thrashes it)
+  const int64_t n_total = NH / H;
+  const int64_t per_cta = RANGE ? (n_total + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t r_beg = RANGE ? (int64_t)blockIdx.x * per_cta : 0;
+  const int64_t r_cnt = RANGE ? max((int64_t)0, min(n_total, r_beg + per_cta) - r_beg) : 0;
+  const int64_t i_beg = RANGE ? (int64_t)(threadIdx.x >> 5) : ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  const int64_t i_end = RANGE ? r_cnt * H : NH;
+  const int64_t i_step = RANGE ? (int64_t)(blockDim.x >> 5) : (((int64_t)gridDim.x * blockDim.x) >> 5);
+  for (int64_t i = i_beg; i < i_end; i += i_step) {
+    const int h = RANGE ? (int)(i / r_cnt) : (int)(i % H);
+    const int64_t u = RANGE ? r_beg + (i - (int64_t)h * r_cnt) : i / H;
+    const int64_t w = u * H + h;
     const int32_t beg = cptr[u], end = cptr[u + 1];
     const float elu_ = el[w];
     RowFrag<VEC, VECTOR> acc;
@@ -308,6 +338,44 @@ __global__ void gat_attn_grad_partial_kernel(const float* __restrict__ Z, int64_
     partial[(int64_t)blockIdx.x * HF + c] = s;
   }
 }
+// Both attention-vector gradients in ONE pass over Z: dal[h,f] = sum_u del[u,h] Z[u,h,f], dar likewise with der.
+// Thread = 4 consecutive columns (float4), 8 rows in flight; HF % 4 == 0 and 16-byte aligned rows.
+__global__ void __launch_bounds__(256)
+gat_attn_grad2_partial_kernel(const float* __restrict__ Z, int64_t ldz, const float* __restrict__ cl,
+                              const float* __restrict__ cr, int64_t N, int H, int F, int64_t rows_per_block,
+                              float* __restrict__ partial_l, float* __restrict__ partial_r) {
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < N ? r0 + rows_per_block : N;
+  const int HF4 = H * F / 4;
+  for (int c4 = threadIdx.x; c4 < HF4; c4 += blockDim.x) {
+    const int h = c4 * 4 / F;
+    float4 sl = make_float4(0.f, 0.f, 0.f, 0.f), sr = sl;
+    int64_t r = r0;
+    for (; r + 8 <= r1; r += 8) {
+      float4 z[8];
+      float a[8], b[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        z[j] = ldg_nc_na(reinterpret_cast<const float4*>(Z + (r + j) * ldz) + c4);
+        a[j] = __ldg(cl + (r + j) * H + h);
+        b[j] = __ldg(cr + (r + j) * H + h);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sl.x = fmaf(a[j], z[j].x, sl.x); sl.y = fmaf(a[j], z[j].y, sl.y); sl.z = fmaf(a[j], z[j].z, sl.z); sl.w = fmaf(a[j], z[j].w, sl.w);
+        sr.x = fmaf(b[j], z[j].x, sr.x); sr.y = fmaf(b[j], z[j].y, sr.y); sr.z = fmaf(b[j], z[j].z, sr.z); sr.w = fmaf(b[j], z[j].w, sr.w);
+      }
+    }
+    for (; r < r1; ++r) {
+      const float4 z = ldg_nc_na(reinterpret_cast<const float4*>(Z + r * ldz) + c4);
+      const float a = __ldg(cl + r * H + h), b = __ldg(cr + r * H + h);
+      sl.x = fmaf(a, z.x, sl.x); sl.y = fmaf(a, z.y, sl.y); sl.z = fmaf(a, z.z, sl.z); sl.w = fmaf(a, z.w, sl.w);
+      sr.x = fmaf(b, z.x, sr.x); sr.y = fmaf(b, z.y, sr.y); sr.z = fmaf(b, z.z, sr.z); sr.w = fmaf(b, z.w, sr.w);
+    }
+    reinterpret_cast<float4*>(partial_l + (int64_t)blockIdx.x * H * F)[c4] = sl;
+    reinterpret_cast<float4*>(partial_r + (int64_t)blockIdx.x * H * F)[c4] = sr;
+  }
+}
 __global__ void gat_attn_grad_final_kernel(const float* __restrict__ partial, int n_blocks, int HF, float* __restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= HF) return;
@@ -333,15 +401,28 @@ static inline int attn_blocks(int64_t N) {
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // Dispatch on (F, alignment): float4 lanes when possible.
+#define GAT_DISPATCH_R(KERNEL, R, TH, vec_ok, F, ...)                                               \
+  do {                                                                                              \
+    if ((vec_ok) && (F) <= 128)       KERNEL<1, true, R><<<grid, TH, 0, st>>>(__VA_ARGS__);         \
+    else if ((vec_ok) && (F) <= 256)  KERNEL<2, true, R><<<grid, TH, 0, st>>>(__VA_ARGS__);         \
+    else if ((vec_ok) && (F) <= 512)  KERNEL<4, true, R><<<grid, TH, 0, st>>>(__VA_ARGS__);         \
+    else if ((F) <= 128)              KERNEL<1, false, R><<<grid, TH, 0, st>>>(__VA_ARGS__);        \
+    else if ((F) <= 256)              KERNEL<2, false, R><<<grid, TH, 0, st>>>(__VA_ARGS__);        \
+    else if ((F) <= 512)              KERNEL<4, false, R><<<grid, TH, 0, st>>>(__VA_ARGS__);        \
+    else { set_error("GAT kernels support F <= 512 (got %d)", (int)(F)); return GTS_ERR_UNSUPPORTED; } \
+  } while (0)
+// head-major contiguous ranges (one 1024-thread CTA per SM) when there is at least one full sweep of nodes per SM;
+// GTS_GAT_RANGE=0 keeps the grid-stride distribution (A/B switch)
 #define GAT_DISPATCH(KERNEL, vec_ok, F, ...)                                                        \
   do {                                                                                              \
-    if ((vec_ok) && (F) <= 128)       KERNEL<1, true><<<grid, kGatThreads, 0, st>>>(__VA_ARGS__);   \
-    else if ((vec_ok) && (F) <= 256)  KERNEL<2, true><<<grid, kGatThreads, 0, st>>>(__VA_ARGS__);   \
-    else if ((vec_ok) && (F) <= 512)  KERNEL<4, true><<<grid, kGatThreads, 0, st>>>(__VA_ARGS__);   \
-    else if ((F) <= 128)              KERNEL<1, false><<<grid, kGatThreads, 0, st>>>(__VA_ARGS__);  \
-    else if ((F) <= 256)              KERNEL<2, false><<<grid, kGatThreads, 0, st>>>(__VA_ARGS__);  \
-    else if ((F) <= 512)              KERNEL<4, false><<<grid, kGatThreads, 0, st>>>(__VA_ARGS__);  \
-    else { set_error("GAT kernels support F <= 512 (got %d)", (int)(F)); return GTS_ERR_UNSUPPORTED; } \
+    static const bool range_off = getenv("GTS_GAT_RANGE") && atoi(getenv("GTS_GAT_RANGE")) == 0;    \
+    if (!range_off && NH / H >= (int64_t)sm_count() * 32) {                                         \
+      const int grid = sm_count();                                                                  \
+      GAT_DISPATCH_R(KERNEL, true, 1024, vec_ok, F, __VA_ARGS__);                                   \
+    } else {                                                                                        \
+      const int grid = gat_grid(NH);                                                                \
+      GAT_DISPATCH_R(KERNEL, false, kGatThreads, vec_ok, F, __VA_ARGS__);                           \
+    }                                                                                               \
   } while (0)
 
 }  // namespace gts
@@ -373,7 +454,6 @@ int gts_gat_fwd(const float* Z, int64_t ldz, const float* el, const float* er,
   GTS_CHECK_ARG(Z && el && er && indptr && out && rowmax && rowsum && err_flag, "gts_gat_fwd: null pointer");
   cudaStream_t st = as_stream(stream);
   const int64_t NH = (int64_t)n_nodes * H;
-  const int grid = gat_grid(NH);
   const bool vec_ok = (F % 4 == 0) && (ldz % 4 == 0) && (ldo % 4 == 0) && al16(Z) && al16(out) &&
                       (!res || ((ldres % 4 == 0) && al16(res))) && (!bias || al16(bias));
   GAT_DISPATCH(gat_fwd_kernel, vec_ok, F, Z, ldz, el, er, indptr, indices, NH, H, F, slope, res, ldres, bias, act,
@@ -405,7 +485,6 @@ int gts_gat_bwd_dst(const float* Z, int64_t ldz, const float* el, const float* e
   GTS_CHECK_ARG(Z && el && er && rowmax && rowsum && indptr && dO && dt_edge && der, "gts_gat_bwd_dst: null pointer");
   cudaStream_t st = as_stream(stream);
   const int64_t NH = (int64_t)n_nodes * H;
-  const int grid = gat_grid(NH);
   const bool vec_ok = (F % 4 == 0) && (ldz % 4 == 0) && (lddo % 4 == 0) && al16(Z) && al16(dO);
   GAT_DISPATCH(gat_bwd_dst_kernel, vec_ok, F, Z, ldz, el, er, rowmax, rowsum, indptr, indices, dO, lddo, NH, H, F,
                slope, dt_edge, der);
@@ -425,7 +504,6 @@ int gts_gat_bwd_src(const float* el, const float* er, const float* rowmax, const
                 "gts_gat_bwd_src: null pointer");
   cudaStream_t st = as_stream(stream);
   const int64_t NH = (int64_t)n_nodes * H;
-  const int grid = gat_grid(NH);
   const bool vec_ok = (F % 4 == 0) && (lddo % 4 == 0) && (lddz % 4 == 0) && al16(dO) && al16(dZ) && al16(attn_l) && al16(attn_r);
   GAT_DISPATCH(gat_bwd_src_kernel, vec_ok, F, el, er, rowmax, rowsum, csc_indptr, csc_indices, csc2csr, dO, lddo,
                dt_edge, der, attn_l, attn_r, NH, H, F, slope, dZ, lddz, del);
@@ -460,6 +538,37 @@ int gts_gat_attn_grad(const float* Z, int64_t ldz, const float* coef, int32_t n_
   gat_attn_grad_partial_kernel<<<nb, 256, 0, st>>>(Z, ldz, coef, n_nodes, H, F, rpb, partial);
   GTS_LAUNCH_CHECK();
   gat_attn_grad_final_kernel<<<(H * F + 127) / 128, 128, 0, st>>>(partial, nb, H * F, dattn);
+  GTS_LAUNCH_CHECK();
+  return GTS_OK;
+}
+
+int gts_gat_attn_grad2(const float* Z, int64_t ldz, const float* coef_l, const float* coef_r, int32_t n_nodes,
+                       int32_t H, int32_t F, float* dattn_l, float* dattn_r, void* workspace, size_t workspace_bytes,
+                       gts_stream_t stream) {
+  GTS_CHECK_ARG(n_nodes >= 0 && H >= 1 && F >= 1, "gts_gat_attn_grad2: bad size");
+  GTS_CHECK_ARG(dattn_l && dattn_r, "gts_gat_attn_grad2: null output");
+  const size_t one = gts_gat_attn_grad_workspace_bytes(n_nodes, H, F);
+  const bool vec_ok = n_nodes > 0 && F % 4 == 0 && ldz % 4 == 0 && al16(Z);
+  if (!vec_ok) {       // generic shapes: two passes of the scalar kernel
+    int rc = gts_gat_attn_grad(Z, ldz, coef_l, n_nodes, H, F, dattn_l, workspace, workspace_bytes, stream);
+    if (rc != GTS_OK) return rc;
+    return gts_gat_attn_grad(Z, ldz, coef_r, n_nodes, H, F, dattn_r, workspace, workspace_bytes, stream);
+  }
+  GTS_CHECK_ARG(Z && coef_l && coef_r && workspace, "gts_gat_attn_grad2: null pointer");
+  if (workspace_bytes < 2 * one) {
+    set_error("gts_gat_attn_grad2: workspace %zu < required %zu", workspace_bytes, 2 * one);
+    return GTS_ERR_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  const int nb = attn_blocks(n_nodes);
+  const int64_t rpb = ceil_div<int64_t>(n_nodes, nb);
+  float* pl = reinterpret_cast<float*>(workspace);
+  float* pr = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + one);
+  gat_attn_grad2_partial_kernel<<<nb, 256, 0, st>>>(Z, ldz, coef_l, coef_r, n_nodes, H, F, rpb, pl, pr);
+  GTS_LAUNCH_CHECK();
+  gat_attn_grad_final_kernel<<<(H * F + 127) / 128, 128, 0, st>>>(pl, nb, H * F, dattn_l);
+  GTS_LAUNCH_CHECK();
+  gat_attn_grad_final_kernel<<<(H * F + 127) / 128, 128, 0, st>>>(pr, nb, H * F, dattn_r);
   GTS_LAUNCH_CHECK();
   return GTS_OK;
 }

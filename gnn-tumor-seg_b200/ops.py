@@ -654,14 +654,12 @@ class GatLayerFn(torch.autograd.Function):
         check(lib.gts_gat_bwd_src(ptr(el), ptr(er), ptr(rowmax), ptr(rowsum), ptr(cptr), ptr(cidx), ptr(c2r),
                                   ptr(dR), H * F, ptr(dt), ptr(der), ptr(al), ptr(ar), N, H, F, slope,
                                   ptr(dZ), H * F, ptr(del_), st), "gts_gat_bwd_src")
-        ws = _workspace(lib.gts_gat_attn_grad_workspace_bytes(N, H, F), dev)
+        ws = _workspace(2 * lib.gts_gat_attn_grad_workspace_bytes(N, H, F), dev)
         dal = torch.empty((1, H, F), dtype=torch.float32, device=dev)
         dar = torch.empty((1, H, F), dtype=torch.float32, device=dev)
-        check(lib.gts_gat_attn_grad(ptr(Z), H * F, ptr(del_), N, H, F, ptr(dal), ptr(ws), ws.numel(), st),
-              "gts_gat_attn_grad")
-        check(lib.gts_gat_attn_grad(ptr(Z), H * F, ptr(der), N, H, F, ptr(dar), ptr(ws), ws.numel(), st),
-              "gts_gat_attn_grad")
-        _count(6)
+        check(lib.gts_gat_attn_grad2(ptr(Z), H * F, ptr(del_), ptr(der), N, H, F, ptr(dal), ptr(dar), ptr(ws), ws.numel(), st),
+              "gts_gat_attn_grad2")                       # both attention-vector gradients in one pass over Z
+        _count(5)
         dW = gemm_tn(dZ, x)
         dbias = colsum(dR) if has_bias else None
         dWres = gemm_tn(dR, x) if Wres is not None else None

@@ -343,6 +343,12 @@ GTS_API int gts_gat_attn_grad(const float* Z, int64_t ldz, const float* coef, in
                       int32_t H, int32_t F, float* dattn, void* workspace, size_t workspace_bytes,
                       gts_stream_t stream);
 
+/* Both attention-vector gradients in one pass over Z (dattn_l from coef_l = del, dattn_r from coef_r = der);
+ * workspace: 2 x gts_gat_attn_grad_workspace_bytes. */
+GTS_API int gts_gat_attn_grad2(const float* Z, int64_t ldz, const float* coef_l, const float* coef_r, int32_t n_nodes,
+                       int32_t H, int32_t F, float* dattn_l, float* dattn_r, void* workspace, size_t workspace_bytes,
+                       gts_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Optimiser step on a flat parameter arena (model/gnn_model.py:28,46):
  * AdamW exactly as torch.optim.AdamW (decoupled weight decay, bias
