@@ -190,7 +190,7 @@ def time_kernel(fn, n_iter, stream_sync=True):
 
 def kernel_breakdown(step_fn, ops):
     """One instrumented step: CUDA-event time of every libgts call class."""
-    names = ["gemm_nt", "gemm_tn", "gemm_tn_colsum", "segmax_fwd", "segmax_bwd", "colsum", "transpose", "mask_pos", "ce_weighted",
+    names = ["gemm_nt", "gemm_tn", "gemm_tn_colsum", "gemm_tn2_colsum", "segmax_fwd", "segmax_bwd", "colsum", "transpose", "mask_pos", "ce_weighted",
              "scale_by_inv_"]
     orig = {n: getattr(ops, n) for n in names}
     records = []
@@ -367,8 +367,8 @@ def run_ours(args):
     share = {k: {"ms": round(v["ms"], 4), "calls": v["calls"], "share": round(v["ms"] / tot, 4)}
              for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])}
     dominant = next(iter(share))
-    if dominant in ("gemm_nt", "gemm_tn", "gemm_tn_colsum"):
-        gemm_ms = sum(breakdown.get(k, {"ms": 0})["ms"] for k in ("gemm_nt", "gemm_tn", "gemm_tn_colsum"))
+    if dominant in ("gemm_nt", "gemm_tn", "gemm_tn_colsum", "gemm_tn2_colsum"):
+        gemm_ms = sum(breakdown.get(k, {"ms": 0})["ms"] for k in ("gemm_nt", "gemm_tn", "gemm_tn_colsum", "gemm_tn2_colsum"))
         flops = model_flops_bytes(n_nodes, n_edges)
         ach = flops / (gemm_ms * 1e-3) / 1e12
         roofline = {"kernel": "gemm (tcgen05 tf32)" if args.mode != "fp32" else "gemm (simt fp32)", "bound": "tensor",

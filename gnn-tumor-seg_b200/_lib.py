@@ -72,6 +72,9 @@ _SIGNATURES = {
     "gts_gemm_tn_colsum_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64, C.c_int32]),
     "gts_gemm_tn_colsum": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_int32, C.c_int32,
                                      C.c_int64, C.c_int32, c_f32p, C.c_void_p, C.c_size_t, c_stream]),
+    "gts_gemm_tn2_colsum_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64, C.c_int32]),
+    "gts_gemm_tn2_colsum": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int64,
+                                      C.c_int32, C.c_int32, C.c_int64, C.c_int32, c_f32p, C.c_void_p, C.c_size_t, c_stream]),
     "gts_colsum_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "gts_colsum": (C.c_int, [c_f32p, C.c_int64, C.c_int64, C.c_int32, c_f32p, C.c_void_p, C.c_size_t, c_stream]),
     "gts_transpose": (C.c_int, [c_f32p, C.c_int64, C.c_int32, C.c_int32, c_f32p, C.c_int64, c_stream]),

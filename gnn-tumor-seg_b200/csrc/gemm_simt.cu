@@ -13,6 +13,12 @@ int gemm_tn_tcgen05(const float* A, int64_t lda, const float* B, int64_t ldb, fl
                     int32_t Mo, int32_t No, int64_t K, int32_t mode, float* colsum_out, void* ws, size_t ws_bytes,
                     cudaStream_t st);
 bool gemm_tn_tcgen05_fuses_colsum(int32_t mode);
+bool gemm_tn2_tcgen05_supported(const float* A, int64_t lda, const float* B1, int64_t ldb1, const float* B2, int64_t ldb2,
+                                int32_t Mo, int32_t No, int64_t K, int32_t mode);
+size_t gemm_tn2_tcgen05_ws(int32_t Mo, int32_t No, int64_t K);
+int gemm_tn2_tcgen05(const float* A, int64_t lda, const float* B1, int64_t ldb1, const float* B2, int64_t ldb2,
+                     float* C1, float* C2, int64_t ldc, int32_t Mo, int32_t No, int64_t K, float* colsum_out,
+                     void* ws, size_t ws_bytes, cudaStream_t st);
 size_t gemm_tn_tcgen05_ws(int32_t Mo, int32_t No, int64_t K, int32_t mode);
 bool gemm_nt_tcgen05_supported(const gts_gemm_nt_args* a);
 bool gemm_tn_tcgen05_supported(const float* A, int64_t lda, const float* B, int64_t ldb, int32_t Mo, int32_t No, int64_t K);
@@ -519,6 +525,26 @@ int gts_gemm_tn_colsum(const float* A, int64_t lda, const float* B, int64_t ldb,
   int rc = gts_gemm_tn(A, lda, B, ldb, C, ldc, Mo, No, K, mode, workspace, tn_bytes, stream);
   if (rc != GTS_OK) return rc;
   return gts_colsum(A, lda, K, Mo, colsum_out, reinterpret_cast<char*>(workspace) + tn_bytes, workspace_bytes - tn_bytes, stream);
+}
+
+size_t gts_gemm_tn2_colsum_workspace_bytes(int32_t Mo, int32_t No, int64_t K, int32_t mode) {
+  size_t a = gts_gemm_tn_colsum_workspace_bytes(Mo, No, K, mode);
+  size_t b = mode == GTS_GEMM_TF32X3 ? gemm_tn2_tcgen05_ws(Mo, No, K) : 0;
+  return a > b ? a : b;
+}
+
+int gts_gemm_tn2_colsum(const float* A, int64_t lda, const float* B1, int64_t ldb1, const float* B2, int64_t ldb2,
+                        float* C1, float* C2, int64_t ldc, int32_t Mo, int32_t No, int64_t K, int32_t mode,
+                        float* colsum_out, void* workspace, size_t workspace_bytes, gts_stream_t stream) {
+  GTS_CHECK_ARG(Mo >= 0 && No >= 0 && K >= 0, "gts_gemm_tn2_colsum: negative size");
+  GTS_CHECK_ARG(mode >= GTS_GEMM_FP32 && mode <= GTS_GEMM_TF32X3, "gts_gemm_tn2_colsum: unknown mode %d", mode);
+  if (Mo > 0 && No > 0 && K > 0 && A && B1 && B2 && C1 && C2 && colsum_out &&
+      gemm_tn2_tcgen05_supported(A, lda, B1, ldb1, B2, ldb2, Mo, No, K, mode))
+    return gemm_tn2_tcgen05(A, lda, B1, ldb1, B2, ldb2, C1, C2, ldc, Mo, No, K, colsum_out, workspace, workspace_bytes,
+                            as_stream(stream));
+  int rc = gts_gemm_tn_colsum(A, lda, B1, ldb1, C1, ldc, Mo, No, K, mode, colsum_out, workspace, workspace_bytes, stream);
+  if (rc != GTS_OK) return rc;
+  return gts_gemm_tn(A, lda, B2, ldb2, C2, ldc, Mo, No, K, mode, workspace, workspace_bytes, stream);
 }
 
 size_t gts_colsum_workspace_bytes(int64_t rows, int32_t cols) {

@@ -196,6 +196,7 @@ struct Params {
   const float* bias; const float* bias2; const float* aux; int64_t ldaux; int act;
   // TN (split-K)
   int splits; int kb_per_split; int kb_total; int64_t split_stride;
+  int64_t c2_off;          // TN two-B form: offset (floats) of the second product inside a split record
   float* colsum_partial;   // TN, A-in-TMEM kernel: [splits][M] column sums of the A operand (or null)
 };
 
@@ -776,15 +777,19 @@ gemm_x3ts_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
 // rank 0) only, its a_ready / b_ready / tmem_empty barriers collect (plain, CTA-scope-release) remote arrivals
 // from both CTAs, and tcgen05.commit multicasts "stage free" / "A slot free" / "accumulator full" to both.
 // ---------------------------------------------------------------------------
-struct Ts2Cfg {
+// DUAL (weight gradients only): one A operand against TWO B operands per ring slot (dWs = dZ^T h and dWn = dZ^T neigh
+// share dZ): the split A tile in TMEM feeds 24 instead of 12 MMAs, into two accumulators.
+template <bool DUAL>
+struct Ts2CfgT {
+  static constexpr int NB = DUAL ? 2 : 1;                                // B operands per slot
   static constexpr int BN_MAX = 128;                                   // UMMA N of a pair tile
   static constexpr int KSUB = 1;                                       // k-blocks (of 32) per ring slot: one barrier round per 24 MMAs
-  static constexpr int STAGES = 6;                                     // shared-memory ring
+  static constexpr int STAGES = DUAL ? 4 : 6;                          // shared-memory ring
   static constexpr int A_SLOTS = 4;                                    // TMEM ring of split A tiles
   static constexpr int ACC_BUFS = 2;
   static constexpr int EPI_WARPS = 4;
   static constexpr int B_HALF_BYTES = (BN_MAX / 2) * BK * 4;           // 8 KB: this CTA's half of the N rows
-  static constexpr int SUB_BYTES = A_STAGE_BYTES + 2 * B_HALF_BYTES;   // one k-block: A | B half hi | B half lo = 32 KB
+  static constexpr int SUB_BYTES = A_STAGE_BYTES + NB * 2 * B_HALF_BYTES; // one k-block: A | (B half hi | B half lo) x NB = 32 / 48 KB
   static constexpr int STAGE_BYTES = KSUB * SUB_BYTES;
   static constexpr int THREADS = (10 + EPI_WARPS) * 32;
   static constexpr int epi_off = STAGES * STAGE_BYTES;
@@ -797,6 +802,7 @@ struct Ts2Cfg {
   static constexpr uint32_t A_COL0 = ACC_BUFS * BN_MAX;                // 256
   static_assert(A_COL0 + 64 * KSUB * A_SLOTS <= TMEM_COLS, "TMEM column budget");
 };
+using Ts2Cfg = Ts2CfgT<false>;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -867,11 +873,13 @@ __device__ __forceinline__ void mma_x3_block_ts2(uint32_t d_tmem, uint32_t a_hi,
       ::"r"(d_tmem), "r"(a_hi), "r"(b_lo32), "r"(l_lo32), "r"(desc_hi32), "r"(k16), "r"(idesc), "r"(first) : "memory");
 }
 
-template <bool TN>
+template <bool TN, bool DUAL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Ts2Cfg::THREADS, 1)
 gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, const Params p) {
-  using L = Ts2Cfg;
+  static_assert(!DUAL || TN, "the two-B form exists for the weight-gradient GEMM only");
+  using L = Ts2CfgT<DUAL>;
+  constexpr int NB = L::NB;
   constexpr int STAGES = L::STAGES;
   constexpr int A_SLOTS = L::A_SLOTS;
   constexpr int ACC_BUFS = L::ACC_BUFS;
@@ -925,7 +933,7 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
 
   // work item w -> (pair tile of 256 rows, N tile, split);  tiles_m counts 256-row pair tiles
   const int n_work = TN ? p.tiles_m * p.tiles_n * p.splits : p.tiles_m * p.tiles_n;
-  const uint32_t stage_tx_bytes = (uint32_t)(BM + half_bn) * BK * 4;
+  const uint32_t stage_tx_bytes = (uint32_t)(BM + NB * half_bn) * BK * 4;
 
   auto k_range = [&](int w, int& kb_beg, int& kb_end) {
     kb_beg = 0; kb_end = p.kb1 + p.kb2;
@@ -959,7 +967,9 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
               const int k0 = kj * BK;    // node rows
 #pragma unroll
               for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * 4096, &tmA1, &full_bar[stage], m0 + 32 * c, k0);
-              for (int c = 0; c < half_bn / 32; ++c) tma_load_2d(sb + c * 4096, &tmB1, &full_bar[stage], n0 + 32 * c, k0);
+              for (int b = 0; b < NB; ++b)
+                for (int c = 0; c < half_bn / 32; ++c)
+                  tma_load_2d(sb + b * 2 * L::B_HALF_BYTES + c * 4096, b ? &tmB2 : &tmB1, &full_bar[stage], n0 + 32 * c, k0);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -983,8 +993,8 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       for (int w = cluster_id; w < n_work; w += n_clusters, ++it) {
         int kb_beg, kb_end;
         k_range(w, kb_beg, kb_end);
-        const int acc = it % ACC_BUFS;
-        const uint32_t acc_phase = (uint32_t)(it / ACC_BUFS) & 1;
+        const int acc = DUAL ? 0 : it % ACC_BUFS;              // DUAL: both accumulators belong to the same work item
+        const uint32_t acc_phase = DUAL ? (uint32_t)it & 1 : (uint32_t)(it / ACC_BUFS) & 1;
         if (!mbar_test(&tmem_empty[acc], acc_phase ^ 1)) mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // drained by both CTAs' epilogues
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_u + (uint32_t)acc * L::BN_MAX;
@@ -995,8 +1005,12 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
           for (int j = 0; j < nsub; ++j) {
             const uint32_t b_lo32 = desc0_lo + sb0 + (uint32_t)(stage * STAGE_BYTES + j * SUB_BYTES) / 16;
             const uint32_t a_hi = tmem_u + L::A_COL0 + (uint32_t)(slot * KSUB + j) * 64;
-            mma_x3_block_ts2(d_tmem, a_hi, b_lo32, b_lo32 + (L::B_HALF_BYTES >> 4), desc0_hi, koff16, idesc,
-                             (kb > kb_beg || j > 0) ? 1u : 0u);
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+              const uint32_t bb = b_lo32 + (uint32_t)b * (2 * L::B_HALF_BYTES >> 4);
+              mma_x3_block_ts2(d_tmem + (uint32_t)b * L::BN_MAX, a_hi, bb, bb + (L::B_HALF_BYTES >> 4), desc0_hi, koff16, idesc,
+                               (kb > kb_beg || j > 0) ? 1u : 0u);
+            }
           }
           tcgen05_commit_mc2_elect(empty0 + (uint32_t)stage * 8);    // both CTAs: shared-memory stage reusable
           tcgen05_commit_mc2_elect(afree0 + (uint32_t)slot * 8);     // both CTAs: TMEM A slot (and its ready barrier) reusable
@@ -1082,12 +1096,15 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         const int nsub = min(KSUB, kb_end - kb);
         {
           for (int j = 0; j < nsub; ++j) {
-            const float4* hi = reinterpret_cast<const float4*>(smem + stage * STAGE_BYTES + j * SUB_BYTES + A_STAGE_BYTES);
-            float4* lo = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES + j * SUB_BYTES + A_STAGE_BYTES + L::B_HALF_BYTES);
+            for (int b = 0; b < NB; ++b) {
+              uint8_t* bt = smem + stage * STAGE_BYTES + j * SUB_BYTES + A_STAGE_BYTES + b * 2 * L::B_HALF_BYTES;
+              const float4* hi = reinterpret_cast<const float4*>(bt);
+              float4* lo = reinterpret_cast<float4*>(bt + L::B_HALF_BYTES);
 #pragma unroll 4
-            for (int i = t; i < n_vec; i += 128) {
-              const float4 x = hi[i];
-              lo[i] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+              for (int i = t; i < n_vec; i += 128) {
+                const float4 x = hi[i];
+                lo[i] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+              }
             }
           }
         }
@@ -1114,9 +1131,12 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       const int m0 = (tile / p.tiles_n) * (2 * BM) + (int)rank * BM + q * 32;
       const int n0 = (tile % p.tiles_n) * p.BN;
       float* Cout = p.C + (TN ? (int64_t)split * p.split_stride : 0);
-      const int acc = it % ACC_BUFS;
+      const int acc = DUAL ? 0 : it % ACC_BUFS;
+      const uint32_t full_phase = DUAL ? (uint32_t)it & 1 : (uint32_t)(it / ACC_BUFS) & 1;
       const uint32_t t_base = tmem_base + (uint32_t)acc * L::BN_MAX + ((uint32_t)(q * 32) << 16);
-      epilogue_tile<TN>(p, t_base, m0, n0, Cout, stg, lane, 0, 32, masked, &tmem_full[acc], (uint32_t)(it / ACC_BUFS) & 1);
+      epilogue_tile<TN>(p, t_base, m0, n0, Cout, stg, lane, 0, 32, masked, &tmem_full[acc], full_phase);
+      if (DUAL)      // second product of the pair (same A): its own accumulator and its own block of the split record
+        epilogue_tile<TN>(p, t_base + L::BN_MAX, m0, n0, Cout + p.c2_off, stg, lane, 0, 32, false, &tmem_full[acc], full_phase);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(tmem_empty_leader + (uint32_t)acc * 8);
@@ -1213,19 +1233,19 @@ static int launch_ts(const CUtensorMap& a1, const CUtensorMap& a2, const CUtenso
   return GTS_OK;
 }
 
-template <bool TN>
+template <bool TN, bool DUAL = false>
 static int launch_ts2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1, const CUtensorMap& b2,
                       const Params& p, int n_work, cudaStream_t st) {
-  using L = Ts2Cfg;
+  using L = Ts2CfgT<DUAL>;
   static bool done = false;
   if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_x3ts2_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::dyn_bytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_x3ts2_kernel<TN, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::dyn_bytes);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d) failed: %s", L::dyn_bytes, cudaGetErrorString(e)); return GTS_ERR_CUDA; }
     done = true;
   }
   const int pairs = sm_count() / 2;
   const int grid = 2 * (n_work < pairs ? n_work : pairs);          // one CTA pair (cluster of 2) per TPC
-  gemm_x3ts2_kernel<TN><<<grid, L::THREADS, L::dyn_bytes, st>>>(a1, a2, b1, b2, p);
+  gemm_x3ts2_kernel<TN, DUAL><<<grid, L::THREADS, L::dyn_bytes, st>>>(a1, a2, b1, b2, p);
   GTS_LAUNCH_CHECK();
   return GTS_OK;
 }
@@ -1381,6 +1401,54 @@ int gemm_tn_tcgen05(const float* A, int64_t lda, const float* B, int64_t ldb, fl
     launch_splitk_reduce(cs_partial, record, p.splits, 1, Mo, colsum_out, Mo, st);
     GTS_LAUNCH_CHECK();
   }
+  return GTS_OK;
+}
+
+// [C1 | C2] = A^T [B1 | B2] (+ column sums of A) in one pass over A; CTA-pair 3xTF32 kernel only.
+bool gemm_tn2_tcgen05_supported(const float* A, int64_t lda, const float* B1, int64_t ldb1, const float* B2, int64_t ldb2,
+                                int32_t Mo, int32_t No, int64_t K, int32_t mode) {
+  return mode == GTS_GEMM_TF32X3 && tc::x3_in_tmem() && tc::tn_pair_shape(Mo, No) && Mo % 4 == 0 &&
+         gemm_tn_tcgen05_supported(A, lda, B1, ldb1, Mo, No, K) && tc::operand_ok(B2, ldb2);
+}
+size_t gemm_tn2_tcgen05_ws(int32_t Mo, int32_t No, int64_t K) {
+  if (Mo < 1 || No < 1 || K < 1) return 0;
+  tc::Params p{};
+  tn_plan(Mo, No, K, GTS_GEMM_TF32X3, p);
+  return align_up((size_t)p.splits * (size_t)(tn_record(Mo, No) + (int64_t)Mo * No) * sizeof(float), 256);
+}
+int gemm_tn2_tcgen05(const float* A, int64_t lda, const float* B1, int64_t ldb1, const float* B2, int64_t ldb2,
+                     float* C1, float* C2, int64_t ldc, int32_t Mo, int32_t No, int64_t K, float* colsum_out,
+                     void* ws, size_t ws_bytes, cudaStream_t st) {
+  using namespace tc;
+  Params p{};
+  tn_plan(Mo, No, K, GTS_GEMM_TF32X3, p);
+  const int64_t prod = (int64_t)Mo * No;
+  const int64_t record = tn_record(Mo, No) + prod;               // [C1 | C2 | column sums]
+  const size_t need = align_up((size_t)p.splits * (size_t)record * sizeof(float), 256);
+  if (!ws || ws_bytes < need) { set_error("gts_gemm_tn2: workspace %zu < required %zu", ws_bytes, need); return GTS_ERR_WORKSPACE; }
+  p.M = Mo; p.N = No;
+  p.C = reinterpret_cast<float*>(ws); p.ldc = No;
+  p.split_stride = record;
+  p.c2_off = prod;
+  float* cs_partial = p.C + 2 * prod;
+  p.colsum_partial = colsum_out ? cs_partial : nullptr;
+  CUtensorMap tA, tB1, tB2;
+  if (!encode_2d(&tA, A, K, Mo, lda, 32, BK, false, true)) return GTS_ERR_CUDA;
+  if (!encode_2d(&tB1, B1, K, No, ldb1, 32, BK, false, true)) return GTS_ERR_CUDA;
+  if (!encode_2d(&tB2, B2, K, No, ldb2, 32, BK, false, true)) return GTS_ERR_CUDA;
+  const int n_work = p.tiles_m * p.tiles_n * p.splits;
+  int rc = launch_ts2<true, true>(tA, tA, tB1, tB2, p, n_work, st);
+  if (rc != GTS_OK) return rc;
+  const bool contiguous = C2 == C1 + prod && ldc == No;
+  if (contiguous && colsum_out && p.splits >= 8 && splitk_reduce_fused_ok(2 * Mo, No, ldc, Mo, record, p.C, C1, colsum_out)) {
+    launch_splitk_reduce_fused(p.C, record, p.splits, 2 * Mo, No, C1, colsum_out, Mo, st);   // one reduction for all three
+    GTS_LAUNCH_CHECK();
+    return GTS_OK;
+  }
+  launch_splitk_reduce(p.C, record, p.splits, Mo, No, C1, ldc, st);
+  launch_splitk_reduce(p.C + prod, record, p.splits, Mo, No, C2, ldc, st);
+  if (colsum_out) launch_splitk_reduce(cs_partial, record, p.splits, 1, Mo, colsum_out, Mo, st);
+  GTS_LAUNCH_CHECK();
   return GTS_OK;
 }
 

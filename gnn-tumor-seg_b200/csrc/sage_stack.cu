@@ -48,7 +48,7 @@ static bool make_plan(const gts_sage_layer* layers, int L, int64_t N, bool train
     }
     size_t gw = 256, cw = 256;
     for (int l = 0; l < L; ++l) {
-      size_t a = gts_gemm_tn_colsum_workspace_bytes(layers[l].dout, layers[l].din, N, mode);
+      size_t a = gts_gemm_tn2_colsum_workspace_bytes(layers[l].dout, layers[l].din, N, mode);
       size_t b = gts_gemm_tn_colsum_workspace_bytes(layers[l].din, layers[l].din, N, mode);
       gw = a > gw ? a : gw; gw = b > gw ? b : gw;
       size_t c = gts_colsum_workspace_bytes(N, layers[l].dout), d = gts_colsum_workspace_bytes(N, layers[l].din);
@@ -187,9 +187,9 @@ int gts_sage_backward(const gts_sage_layer* layers, const gts_sage_layer_grads* 
     const int32_t* arg = reinterpret_cast<const int32_t*>(at(workspace, pl.arg[l]));
     void* gws = at(workspace, pl.gemm_ws);
     // (dZ already carries this layer's ReLU mask: the consumer's epilogue applied (out > 0))
-    // dWs = dZ^T h and db = column sums of dZ (one pass over dZ in the 3xTF32 mode)
-    GTS_TRY(gts_gemm_tn_colsum(dZ, ldz, h, ldh, g.dWs, ly.din, ly.dout, ly.din, N, mode, g.db, gws, pl.gemm_ws_bytes, stream));
-    GTS_TRY(gts_gemm_tn(dZ, ldz, neigh, ly.din, g.dWn, ly.din, ly.dout, ly.din, N, mode, gws, pl.gemm_ws_bytes, stream));
+    // dWs = dZ^T h, dWn = dZ^T neigh and db = column sums of dZ: one pass over dZ in the 3xTF32 mode
+    GTS_TRY(gts_gemm_tn2_colsum(dZ, ldz, h, ldh, neigh, ly.din, g.dWs, g.dWn, ly.din, ly.dout, ly.din, N, mode, g.db, gws,
+                                pl.gemm_ws_bytes, stream));
     // dNeigh' = (dZ Wn) * (neigh > 0)
     const float* WnT = at(workspace, pl.wnT[l]);
     // Measured (profiles/r01_gemm_x3_pipeline.md): routing the masked tile through the arg-max from inside the GEMM

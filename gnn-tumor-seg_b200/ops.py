@@ -252,6 +252,27 @@ def gemm_tn_colsum(A, B, mode=None):
     return out, cs
 
 
+def gemm_tn2_colsum(A, B1, B2, mode=None):
+    """(A.T @ B1, A.T @ B2, A.sum(0)) in one pass over A (tf32x3: the CTA-pair kernel feeds both products from the
+    same split A tile in tensor memory).  The two products are the halves of ONE [2, Mo, No] buffer."""
+    require_cuda(A, B1, B2)
+    lib = _lib.load()
+    A = _row_major_2d(A)
+    B1 = _row_major_2d(B1)
+    B2 = _row_major_2d(B2)
+    K, Mo = A.shape
+    No = B1.shape[1]
+    assert B1.shape == B2.shape and B1.shape[0] == K
+    m = _gemm_mode if mode is None else (GEMM_MODES[mode] if isinstance(mode, str) else mode)
+    out = torch.empty((2, Mo, No), dtype=torch.float32, device=A.device)
+    cs = torch.empty(Mo, dtype=torch.float32, device=A.device)
+    ws = _workspace(lib.gts_gemm_tn2_colsum_workspace_bytes(Mo, No, K, m), A.device)
+    check(lib.gts_gemm_tn2_colsum(ptr(A), _ld(A), ptr(B1), _ld(B1), ptr(B2), _ld(B2), ptr(out[0]), ptr(out[1]), No,
+                                  Mo, No, K, m, ptr(cs), ptr(ws), ws.numel(), stream_ptr()), "gts_gemm_tn2_colsum")
+    _count(2)
+    return out[0], out[1], cs
+
+
 def colsum(A):
     require_cuda(A)
     lib = _lib.load()
@@ -441,8 +462,7 @@ class SagePoolLayerFn(torch.autograd.Function):
         relu_out, input_is_relu, grad_premasked, deterministic = ctx.flags
         dOut = _row_major_2d(dOut)
         dZ = mask_pos(dOut, out) if (relu_out and not grad_premasked) else dOut
-        dWs, db = gemm_tn_colsum(dZ, h)
-        dWn = gemm_tn(dZ, neigh)
+        dWs, dWn, db = gemm_tn2_colsum(dZ, h, neigh)        # one pass over dZ
         # dNeigh' = (dZ Wn) * (neigh > 0): ReLU mask of fc_pool folded here, since
         # neigh[v,k] = P[arg[v,k],k] (Appendix A.1)
         dNeigh = gemm_nt(dZ, transpose(Wn), act=ACT_MASK_POS, aux=neigh)

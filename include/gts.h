@@ -141,6 +141,15 @@ GTS_API int gts_gemm_tn_colsum(const float* A, int64_t lda, const float* B, int6
                        float* C, int64_t ldc, int32_t Mo, int32_t No, int64_t K, int32_t mode,
                        float* colsum_out, void* workspace, size_t workspace_bytes, gts_stream_t stream);
 
+/* Two weight gradients that share their A operand, plus its column sums, in ONE pass over A:
+ * C1 = A^T B1, C2 = A^T B2, colsum_out[m] = sum_k A[k,m]  (dWs = dZ^T h, dWn = dZ^T neigh, db = sum dZ of one
+ * SAGEConv layer).  3xTF32 CTA-pair kernel: the split A tile staged in tensor memory feeds both products;
+ * other modes / shapes: gts_gemm_tn_colsum + gts_gemm_tn behind the same entry point. */
+GTS_API size_t gts_gemm_tn2_colsum_workspace_bytes(int32_t Mo, int32_t No, int64_t K, int32_t mode);
+GTS_API int gts_gemm_tn2_colsum(const float* A, int64_t lda, const float* B1, int64_t ldb1, const float* B2, int64_t ldb2,
+                        float* C1, float* C2, int64_t ldc, int32_t Mo, int32_t No, int64_t K, int32_t mode,
+                        float* colsum_out, void* workspace, size_t workspace_bytes, gts_stream_t stream);
+
 /* out[c] = sum_r A[r,c]  (bias gradients).  Deterministic two-pass. */
 GTS_API size_t gts_colsum_workspace_bytes(int64_t rows, int32_t cols);
 GTS_API int gts_colsum(const float* A, int64_t lda, int64_t rows, int32_t cols, float* out,

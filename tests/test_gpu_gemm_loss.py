@@ -62,6 +62,21 @@ def test_gemm_tn_colsum(cuda_dev, mode, K, Mo, No):
     assert _rel(cs.cpu(), A.double().sum(0)) < 1e-5          # column sums are plain fp32 adds in every mode
 
 
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3", "tf32"])
+@pytest.mark.parametrize("K,Mo,No", [(90000, 256, 256), (5000, 256, 128), (1234, 4, 256), (777, 256, 20), (40001, 192, 64)])
+def test_gemm_tn2_colsum(cuda_dev, mode, K, Mo, No):
+    """Two weight gradients sharing A + its column sums from one entry point (one pass over A in tf32x3)."""
+    g = torch.Generator().manual_seed(K + 3 * Mo + No)
+    A = torch.randn(K, Mo, generator=g); B1 = torch.randn(K, No, generator=g); B2 = torch.randn(K, No, generator=g)
+    c1, c2, cs = ops.gemm_tn2_colsum(A.to(cuda_dev), B1.to(cuda_dev), B2.to(cuda_dev), mode=mode)
+    assert _rel(c1.cpu(), A.double().T @ B1.double()) < TOL[mode]
+    assert _rel(c2.cpu(), A.double().T @ B2.double()) < TOL[mode]
+    assert _rel(cs.cpu(), A.double().sum(0)) < 1e-5
+    Ai = torch.randint(-3, 4, (3000, 256), generator=g).float(); Bi = torch.randint(-3, 4, (3000, 256), generator=g).float()
+    c1, c2, cs = ops.gemm_tn2_colsum(Ai.to(cuda_dev), Bi.to(cuda_dev), Ai.to(cuda_dev), mode=mode)
+    assert torch.equal(c1.cpu(), Ai.T @ Bi) and torch.equal(c2.cpu(), Ai.T @ Ai) and torch.equal(cs.cpu(), Ai.sum(0))
+
+
 def test_gemm_tn_colsum_integer_exact(cuda_dev):
     """Integer-valued operands: products and sums are exact in every arithmetic mode -> bit-exact."""
     g = torch.Generator().manual_seed(3)
