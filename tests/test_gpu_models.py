@@ -283,3 +283,20 @@ def test_full_config_7x256_one_graph_inference(cuda_dev):
         rl = ref((indptr, indices), feats)
     assert _rel(logits, rl) < 1e-4
     assert (logits.argmax(1) == rl.argmax(1)).float().mean().item() >= 0.9999
+
+
+def test_run_epoch_trains(cuda_dev):
+    """GNN.run_epoch (the reference's entry point, model/gnn_model.py:34-48) over a list dataset of host graphs:
+    DataLoader + minibatch_graphs collate, .to(device) with the device CSR build, fwd, weighted CE, bwd, AdamW."""
+    from collections import namedtuple
+    from gnn_tumor_seg_b200.gnn_model import GNN
+    graphs = [synth.make_small_graph(s, n_nodes=400 + 37 * s, avg_deg=9) for s in range(7)]
+    samples = [(g.mri_id, G.from_edge_list(g.src, g.dst, g.n_nodes), g.features, g.labels) for g in graphs]
+    HP = namedtuple("HP", "in_feats out_classes layer_sizes gat_heads gat_residuals class_weights lr w_decay lr_decay")
+    hp = HP(20, 4, [256], None, None, [0.1, 1.0, 2.0, 2.0], 1e-3, 1e-4, 0.98)
+    torch.manual_seed(0)
+    model = GNN("GSpool", hp, samples)
+    l0 = model.run_epoch()
+    for _ in range(4):
+        l1 = model.run_epoch()
+    assert np.isfinite(l0) and np.isfinite(l1) and l1 < l0     # it learns the (random) labels a little
