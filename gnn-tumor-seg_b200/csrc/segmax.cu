@@ -18,11 +18,26 @@ namespace gts {
 
 constexpr int kSegThreads = 256;
 
-__device__ __forceinline__ void fold_max(float4& best, int4& arg, const float4& v, int u) {
-  if (v.x > best.x) { best.x = v.x; arg.x = u; }
-  if (v.y > best.y) { best.y = v.y; arg.y = u; }
-  if (v.z > best.z) { best.z = v.z; arg.z = u; }
-  if (v.w > best.w) { best.w = v.w; arg.w = u; }
+// The arg-max fold is `if (v > best) { best = v; arg = u; }` per element.  Written plainly it compiles to
+// FSETP + FSEL + SEL, all three on the half-rate ALU pipe, and the kernel is bound by that pipe (ncu: pipe_alu 82 %,
+// pipe_fma 9 %).  Here the two selects are predicated FFMA / IMAD with operands the compiler cannot fold
+// (v * 1.0f + -0.0f == v and arg * 0 + u == u exactly, for every v incl. signed zeros, infinities, denormals; the
+// constants arrive as kernel parameters): one ALU instruction and two on the otherwise idle FMA pipe per element.
+struct FoldConst { float one, neg_zero; int zero; };
+static inline FoldConst fold_const() { return FoldConst{1.0f, -0.0f, 0}; }
+
+__device__ __forceinline__ void fold_one(float& best, int& arg, float v, int u, const FoldConst& k) {
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.gt.f32 p, %2, %0;\n\t"
+      "@p fma.rn.f32 %0, %2, %4, %5;\n\t"
+      "@p mad.lo.s32 %1, %1, %6, %3;\n\t}"
+      : "+f"(best), "+r"(arg) : "f"(v), "r"(u), "f"(k.one), "f"(k.neg_zero), "r"(k.zero));
+}
+__device__ __forceinline__ void fold_max(float4& best, int4& arg, const float4& v, int u, const FoldConst& k) {
+  fold_one(best.x, arg.x, v.x, u, k);
+  fold_one(best.y, arg.y, v.y, u, k);
+  fold_one(best.z, arg.z, v.z, u, k);
+  fold_one(best.w, arg.w, v.w, u, k);
 }
 
 // LPN lanes per node (power of two <= 32), VEC float4 chunks per lane:
@@ -37,7 +52,7 @@ __global__ void __launch_bounds__(THREADS)
 segmax_fwd_vec_kernel(const float* __restrict__ P, int64_t ldp, const int32_t* __restrict__ indptr,
                       const int32_t* __restrict__ indices, int32_t N, int32_t D4,
                       float* __restrict__ neigh, int64_t ldn, int32_t* __restrict__ argmax, int64_t ldarg,
-                      int64_t nodes_per_cta) {
+                      int64_t nodes_per_cta, const FoldConst fc) {
   constexpr int NPW = 32 / LPN;   // nodes per warp
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPN;
@@ -90,7 +105,7 @@ segmax_fwd_vec_kernel(const float* __restrict__ P, int64_t ldp, const int32_t* _
           if (u[q] >= 0) {
 #pragma unroll
             for (int c = 0; c < VEC; ++c)
-              if (sub + c * LPN < D4) fold_max(best[c], arg[c], r[q][c], u[q]);
+              if (sub + c * LPN < D4) fold_max(best[c], arg[c], r[q][c], u[q], fc);
           }
         }
       }
@@ -126,7 +141,7 @@ __global__ void __launch_bounds__(kWideWarps * 32, 1)
 segmax_fwd_wide_kernel(const float* __restrict__ P, int64_t ldp, const int32_t* __restrict__ indptr,
                        const int32_t* __restrict__ indices, int32_t N,
                        float* __restrict__ neigh, int64_t ldn, int32_t* __restrict__ argmax, int64_t ldarg,
-                       int64_t nodes_per_cta) {
+                       int64_t nodes_per_cta, const FoldConst fc) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const unsigned full = 0xffffffffu;
@@ -167,10 +182,10 @@ segmax_fwd_wide_kernel(const float* __restrict__ P, int64_t ldp, const int32_t* 
         for (int c = 0; c < VEC; ++c) { r2[c] = ldg_nc(p2 + 32 * c); r3[c] = ldg_nc(p3 + 32 * c); }
 #pragma unroll
         for (int c = 0; c < VEC; ++c) {
-          fold_max(best[c], arg[c], r0[c], u0);
-          fold_max(best[c], arg[c], r1[c], u1);
-          fold_max(best[c], arg[c], r2[c], u2);
-          fold_max(best[c], arg[c], r3[c], u3);
+          fold_max(best[c], arg[c], r0[c], u0, fc);
+          fold_max(best[c], arg[c], r1[c], u1, fc);
+          fold_max(best[c], arg[c], r2[c], u2, fc);
+          fold_max(best[c], arg[c], r3[c], u3, fc);
         }
       }
     }
@@ -192,9 +207,9 @@ static int launch_fwd_wide(const float* P, int64_t ldp, const int32_t* indptr, c
   const int64_t per_cta = ceil_div<int64_t>(N, grid);
   grid = ceil_div<int64_t>(N, per_cta);
   if (argmax)
-    segmax_fwd_wide_kernel<VEC, true, kWideWarps><<<dim3((unsigned)grid, slabs), kWideWarps * 32, 0, st>>>(P, ldp, indptr, indices, N, neigh, ldn, argmax, ldarg, per_cta);
+    segmax_fwd_wide_kernel<VEC, true, kWideWarps><<<dim3((unsigned)grid, slabs), kWideWarps * 32, 0, st>>>(P, ldp, indptr, indices, N, neigh, ldn, argmax, ldarg, per_cta, fold_const());
   else
-    segmax_fwd_wide_kernel<VEC, false, kWideWarps><<<dim3((unsigned)grid, slabs), kWideWarps * 32, 0, st>>>(P, ldp, indptr, indices, N, neigh, ldn, nullptr, 0, per_cta);
+    segmax_fwd_wide_kernel<VEC, false, kWideWarps><<<dim3((unsigned)grid, slabs), kWideWarps * 32, 0, st>>>(P, ldp, indptr, indices, N, neigh, ldn, nullptr, 0, per_cta, fold_const());
   GTS_LAUNCH_CHECK();
   return GTS_OK;
 }
@@ -347,9 +362,9 @@ static int launch_fwd_vec(const float* P, int64_t ldp, const int32_t* indptr, co
   per_cta = ceil_div<int64_t>(per_cta, per_pass) * per_pass;         // whole sweeps
   grid = ceil_div<int64_t>(N, per_cta);
   if (argmax)
-    segmax_fwd_vec_kernel<LPN, VEC, true, THREADS><<<(int)grid, THREADS, 0, st>>>(P, ldp, indptr, indices, N, D4, neigh, ldn, argmax, ldarg, per_cta);
+    segmax_fwd_vec_kernel<LPN, VEC, true, THREADS><<<(int)grid, THREADS, 0, st>>>(P, ldp, indptr, indices, N, D4, neigh, ldn, argmax, ldarg, per_cta, fold_const());
   else
-    segmax_fwd_vec_kernel<LPN, VEC, false, THREADS><<<(int)grid, THREADS, 0, st>>>(P, ldp, indptr, indices, N, D4, neigh, ldn, nullptr, 0, per_cta);
+    segmax_fwd_vec_kernel<LPN, VEC, false, THREADS><<<(int)grid, THREADS, 0, st>>>(P, ldp, indptr, indices, N, D4, neigh, ldn, nullptr, 0, per_cta, fold_const());
   GTS_LAUNCH_CHECK();
   return GTS_OK;
 }
