@@ -33,6 +33,10 @@ __device__ __forceinline__ void fold_one(float& best, int& arg, float v, int u, 
       "@p mad.lo.s32 %1, %1, %6, %3;\n\t}"
       : "+f"(best), "+r"(arg) : "f"(v), "r"(u), "f"(k.one), "f"(k.neg_zero), "r"(k.zero));
 }
+// inference (no arg-max wanted): the value alone is one FMNMX per element
+__device__ __forceinline__ void fold_val(float4& best, const float4& v) {
+  best.x = fmaxf(best.x, v.x); best.y = fmaxf(best.y, v.y); best.z = fmaxf(best.z, v.z); best.w = fmaxf(best.w, v.w);
+}
 __device__ __forceinline__ void fold_max(float4& best, int4& arg, const float4& v, int u, const FoldConst& k) {
   fold_one(best.x, arg.x, v.x, u, k);
   fold_one(best.y, arg.y, v.y, u, k);
@@ -182,10 +186,14 @@ segmax_fwd_wide_kernel(const float* __restrict__ P, int64_t ldp, const int32_t* 
         for (int c = 0; c < VEC; ++c) { r2[c] = ldg_nc(p2 + 32 * c); r3[c] = ldg_nc(p3 + 32 * c); }
 #pragma unroll
         for (int c = 0; c < VEC; ++c) {
-          fold_max(best[c], arg[c], r0[c], u0, fc);
-          fold_max(best[c], arg[c], r1[c], u1, fc);
-          fold_max(best[c], arg[c], r2[c], u2, fc);
-          fold_max(best[c], arg[c], r3[c], u3, fc);
+          if (WRITE_ARG) {
+            fold_max(best[c], arg[c], r0[c], u0, fc);
+            fold_max(best[c], arg[c], r1[c], u1, fc);
+            fold_max(best[c], arg[c], r2[c], u2, fc);
+            fold_max(best[c], arg[c], r3[c], u3, fc);
+          } else {
+            fold_val(best[c], r0[c]); fold_val(best[c], r1[c]); fold_val(best[c], r2[c]); fold_val(best[c], r3[c]);
+          }
         }
       }
     }
