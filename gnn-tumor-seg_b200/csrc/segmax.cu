@@ -296,6 +296,72 @@ segmax_bwd_det_kernel(const float* __restrict__ dN, int64_t ldd, const int32_t* 
   }
 }
 
+// K2b, deterministic AND vectorised: the transposed gather in the shape of the forward kernel.  One warp per SOURCE
+// node u on a contiguous id range per SM, lanes own float4 column chunks; for every out-neighbour v (CSC row of u, in
+// edge-id order) the warp reads arg[v, :] (int4 per lane) and adds dN[v, k] where arg[v, k] == u.  The dN chunk is
+// only fetched by lanes with a match in their four columns (~1/4 of them: each (v, k) has exactly one winner among
+// ~15 neighbours).  No zero-fill, no atomics: every dP element is written exactly once, sums run in CSC order, so the
+// gradients are bitwise reproducible.  The adds are predicated FADDs (FMA pipe), the compares ISETPs (ALU pipe).
+template <int VEC>
+__global__ void __launch_bounds__(1024, 1)
+segmax_bwd_gather_wide_kernel(const float* __restrict__ dN, int64_t ldd, const int32_t* __restrict__ arg, int64_t ldarg,
+                              const int32_t* __restrict__ cptr, const int32_t* __restrict__ cidx, int32_t N,
+                              float* __restrict__ dP, int64_t lddp, int64_t nodes_per_cta) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const unsigned full = 0xffffffffu;
+  const int64_t u_begin = (int64_t)blockIdx.x * nodes_per_cta;
+  const int64_t u_end = u_begin + nodes_per_cta < N ? u_begin + nodes_per_cta : N;
+  const char* __restrict__ argl = reinterpret_cast<const char*>(reinterpret_cast<const int4*>(arg) + lane);
+  const char* __restrict__ dNl = reinterpret_cast<const char*>(reinterpret_cast<const float4*>(dN) + lane);
+  const uint32_t lda_bytes = (uint32_t)(ldarg << 2), ldd_bytes = (uint32_t)(ldd << 2);   // host: N * ld * 4 < 2^32
+
+  for (int64_t u64 = u_begin + warp; u64 < u_end; u64 += 32) {
+    const int32_t u = (int32_t)u64;
+    const int32_t beg = cptr[u], end = cptr[u + 1];
+    float4 acc[VEC];
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int32_t base = beg; base < end; base += 32) {
+      const int32_t my_idx = (base + lane < end) ? cidx[base + lane] : 0;
+      const int32_t cnt = min(32, end - base);
+      for (int32_t j = 0; j < cnt; j += 2) {
+        const bool two = j + 1 < cnt;
+        const int32_t v0 = __shfl_sync(full, my_idx, j), v1 = __shfl_sync(full, my_idx, two ? j + 1 : j);
+        const int4* a0p = reinterpret_cast<const int4*>(argl + (uint64_t)(uint32_t)v0 * lda_bytes);
+        const int4* a1p = reinterpret_cast<const int4*>(argl + (uint64_t)(uint32_t)v1 * lda_bytes);
+        int4 a0[VEC], a1[VEC];
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) { a0[c] = __ldg(a0p + 32 * c); a1[c] = __ldg(a1p + 32 * c); }
+        const int32_t m1 = two ? u : -2;                  // a repeated last neighbour must not be counted twice
+        float4 g0[VEC], g1[VEC];
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+          g0[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+          g1[c] = g0[c];
+          if (a0[c].x == u || a0[c].y == u || a0[c].z == u || a0[c].w == u)
+            g0[c] = ldg_nc(reinterpret_cast<const float4*>(dNl + (uint64_t)(uint32_t)v0 * ldd_bytes) + 32 * c);
+          if (a1[c].x == m1 || a1[c].y == m1 || a1[c].z == m1 || a1[c].w == m1)
+            g1[c] = ldg_nc(reinterpret_cast<const float4*>(dNl + (uint64_t)(uint32_t)v1 * ldd_bytes) + 32 * c);
+        }
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+          if (a0[c].x == u) acc[c].x += g0[c].x;
+          if (a0[c].y == u) acc[c].y += g0[c].y;
+          if (a0[c].z == u) acc[c].z += g0[c].z;
+          if (a0[c].w == u) acc[c].w += g0[c].w;
+          if (a1[c].x == m1) acc[c].x += g1[c].x;
+          if (a1[c].y == m1) acc[c].y += g1[c].y;
+          if (a1[c].z == m1) acc[c].z += g1[c].z;
+          if (a1[c].w == m1) acc[c].w += g1[c].w;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) stg_na(reinterpret_cast<float4*>(dP + u64 * lddp) + lane + 32 * c, acc[c]);
+  }
+}
+
 // Sum-type aggregators (mean / gcn) — same traversal, additive fold.
 __global__ void __launch_bounds__(kSegThreads)
 segsum_fwd_kernel(const float* __restrict__ P, int64_t ldp, const int32_t* __restrict__ indptr,
@@ -461,6 +527,23 @@ int gts_segmax_bwd_det(const float* dNeigh, int64_t ldd, const int32_t* argmax, 
   GTS_CHECK_ARG(n_nodes >= 0 && D >= 0, "gts_segmax_bwd_det: negative size");
   if (n_nodes == 0 || D == 0) return GTS_OK;
   GTS_CHECK_ARG(dNeigh && argmax && csc_indptr && dP, "gts_segmax_bwd_det: null pointer");
+  const bool wide_ok = (D == 128 || D == 256) && ldd % 4 == 0 && ldarg % 4 == 0 && lddp % 4 == 0 && aligned16(dNeigh) &&
+                       aligned16(argmax) && aligned16(dP) && (int64_t)n_nodes * ldd * 4 < ((int64_t)1 << 32) &&
+                       (int64_t)n_nodes * ldarg * 4 < ((int64_t)1 << 32);
+  static const bool no_wide = getenv("GTS_SEGMAX_GENERIC") != nullptr;
+  if (wide_ok && !no_wide) {
+    int64_t grid = sm_count();
+    const int64_t per_cta = ceil_div<int64_t>(n_nodes, grid);
+    grid = ceil_div<int64_t>(n_nodes, per_cta);
+    if (D == 256)
+      segmax_bwd_gather_wide_kernel<2><<<(unsigned)grid, 1024, 0, as_stream(stream)>>>(dNeigh, ldd, argmax, ldarg, csc_indptr,
+                                                                                     csc_indices, n_nodes, dP, lddp, per_cta);
+    else
+      segmax_bwd_gather_wide_kernel<1><<<(unsigned)grid, 1024, 0, as_stream(stream)>>>(dNeigh, ldd, argmax, ldarg, csc_indptr,
+                                                                                     csc_indices, n_nodes, dP, lddp, per_cta);
+    GTS_LAUNCH_CHECK();
+    return GTS_OK;
+  }
   segmax_bwd_det_kernel<<<seg_grid(n_nodes), kSegThreads, 0, as_stream(stream)>>>(dNeigh, ldd, argmax, ldarg, csc_indptr,
                                                                                    csc_indices, n_nodes, D, dP, lddp);
   GTS_LAUNCH_CHECK();
