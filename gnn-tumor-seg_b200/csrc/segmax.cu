@@ -445,6 +445,106 @@ static int launch_fwd_vec(const float* P, int64_t ldp, const int32_t* indptr, co
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Sum-type aggregators, wide form (D == 128 * VEC, aligned rows): the traversal of the forward seg-max kernel with an
+// additive fold (8 FADD/FFMA per neighbour and lane, on the FMA pipe).  One kernel for both directions:
+//   forward  (row = destination v over the in-edge CSR):  out[v] = sum_u X[u]            (mode 0)
+//                                                                  / deg(v)              (mode 1, mean)
+//                                                         (sum_u X[u] + X[v]) / (deg+1)  (mode 2, gcn)
+//   backward (row = source u over the out-edge CSC):      out[u] = sum_v s(v) X[v] (+ s(u) X[u] for gcn),
+//            s(v) = 1, 1/deg_in(v), 1/(deg_in(v)+1); deg_in comes from the in-edge indptr `wptr`.
+template <int VEC, bool BACKWARD>
+__global__ void __launch_bounds__(1024, 1)
+segsum_wide_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict__ ptr_,
+                   const int32_t* __restrict__ idx, const int32_t* __restrict__ wptr, int32_t N, int mode,
+                   float* __restrict__ out, int64_t ldo, int64_t nodes_per_cta) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const unsigned full = 0xffffffffu;
+  const int64_t r_begin = (int64_t)blockIdx.x * nodes_per_cta;
+  const int64_t r_end = r_begin + nodes_per_cta < N ? r_begin + nodes_per_cta : N;
+  const char* __restrict__ Xl = reinterpret_cast<const char*>(reinterpret_cast<const float4*>(X) + lane);
+  const uint32_t ld_bytes = (uint32_t)(ldx << 2);
+  auto scale_of = [&](int32_t v) -> float {
+    if (mode == 0) return 1.f;
+    const int32_t d = wptr[v + 1] - wptr[v];
+    return mode == 1 ? (d > 0 ? 1.f / (float)d : 0.f) : 1.f / (float)(d + 1);
+  };
+  for (int64_t r = r_begin + warp; r < r_end; r += 32) {
+    const int32_t beg = ptr_[r], end = ptr_[r + 1];
+    float4 acc[VEC];
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int32_t base = beg; base < end; base += 32) {
+      int32_t my_idx = 0;
+      float my_w = 0.f;                                   // lanes past the row end carry weight 0
+      if (base + lane < end) {
+        my_idx = idx[base + lane];
+        my_w = BACKWARD ? scale_of(my_idx) : 1.f;
+      }
+      const int32_t cnt = min(32, end - base);
+      for (int32_t j = 0; j < cnt; j += 4) {              // a short last group re-reads lane `cnt` onwards: index 0, weight 0
+        int32_t u[4];
+        float w[4];
+        float4 x[4][VEC];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          u[q] = __shfl_sync(full, my_idx, (j + q) & 31);
+          w[q] = __shfl_sync(full, my_w, (j + q) & 31);
+          const float4* p = reinterpret_cast<const float4*>(Xl + (uint64_t)(uint32_t)u[q] * ld_bytes);
+#pragma unroll
+          for (int c = 0; c < VEC; ++c) x[q][c] = ldg_nc(p + 32 * c);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (j + q < cnt) {
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) {
+              acc[c].x = fmaf(w[q], x[q][c].x, acc[c].x); acc[c].y = fmaf(w[q], x[q][c].y, acc[c].y);
+              acc[c].z = fmaf(w[q], x[q][c].z, acc[c].z); acc[c].w = fmaf(w[q], x[q][c].w, acc[c].w);
+            }
+          }
+        }
+      }
+    }
+    const int32_t deg = end - beg;
+    float self_w = 0.f;
+    if (!BACKWARD) {
+      if (mode == 2) self_w = 1.f;
+    } else if (mode == 2) {
+      self_w = scale_of((int32_t)r);
+    }
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+      float4 o = acc[c];
+      if (self_w != 0.f) {
+        const float4 sx = ldg_nc(reinterpret_cast<const float4*>(Xl + (uint64_t)(uint32_t)r * ld_bytes) + 32 * c);
+        o.x = fmaf(self_w, sx.x, o.x); o.y = fmaf(self_w, sx.y, o.y); o.z = fmaf(self_w, sx.z, o.z); o.w = fmaf(self_w, sx.w, o.w);
+      }
+      if (!BACKWARD && mode != 0) {                       // the reference divides: (sum [+ self]) / n
+        const float n = mode == 1 ? (float)deg : (float)(deg + 1);
+        if (mode == 1 && deg == 0) o = make_float4(0.f, 0.f, 0.f, 0.f);
+        else { o.x /= n; o.y /= n; o.z /= n; o.w /= n; }
+      }
+      stg_na(reinterpret_cast<float4*>(out + r * ldo) + lane + 32 * c, o);
+    }
+  }
+}
+
+template <bool BACKWARD>
+static bool launch_segsum_wide(const float* X, int64_t ldx, const int32_t* ptr_, const int32_t* idx, const int32_t* wptr,
+                               int32_t N, int32_t D, int mode, float* out, int64_t ldo, cudaStream_t st) {
+  const bool ok = (D == 128 || D == 256) && ldx % 4 == 0 && ldo % 4 == 0 && aligned16(X) && aligned16(out) &&
+                  (int64_t)N * ldx * 4 < ((int64_t)1 << 32);
+  if (!ok) return false;
+  int64_t grid = sm_count();
+  const int64_t per_cta = ceil_div<int64_t>(N, grid);
+  grid = ceil_div<int64_t>(N, per_cta);
+  if (D == 256) segsum_wide_kernel<2, BACKWARD><<<(unsigned)grid, 1024, 0, st>>>(X, ldx, ptr_, idx, wptr, N, mode, out, ldo, per_cta);
+  else segsum_wide_kernel<1, BACKWARD><<<(unsigned)grid, 1024, 0, st>>>(X, ldx, ptr_, idx, wptr, N, mode, out, ldo, per_cta);
+  return true;
+}
+
+
 }  // namespace gts
 
 using namespace gts;
@@ -556,6 +656,10 @@ int gts_segsum_fwd(const float* P, int64_t ldp, const int32_t* indptr, const int
   GTS_CHECK_ARG(mode >= 0 && mode <= 2, "gts_segsum_fwd: mode must be 0 (sum), 1 (mean) or 2 (gcn)");
   if (n_nodes == 0 || D == 0) return GTS_OK;
   GTS_CHECK_ARG(P && indptr && out, "gts_segsum_fwd: null pointer");
+  if (launch_segsum_wide<false>(P, ldp, indptr, indices, indptr, n_nodes, D, mode, out, ldo, as_stream(stream))) {
+    GTS_LAUNCH_CHECK();
+    return GTS_OK;
+  }
   segsum_fwd_kernel<<<seg_grid(n_nodes), kSegThreads, 0, as_stream(stream)>>>(P, ldp, indptr, indices, n_nodes, D, mode, out, ldo);
   GTS_LAUNCH_CHECK();
   return GTS_OK;
@@ -568,6 +672,10 @@ int gts_segsum_bwd(const float* dOut, int64_t ldd, const int32_t* csc_indptr, co
   GTS_CHECK_ARG(mode >= 0 && mode <= 2, "gts_segsum_bwd: mode must be 0, 1 or 2");
   if (n_nodes == 0 || D == 0) return GTS_OK;
   GTS_CHECK_ARG(dOut && csc_indptr && in_indptr && dP, "gts_segsum_bwd: null pointer");
+  if (launch_segsum_wide<true>(dOut, ldd, csc_indptr, csc_indices, in_indptr, n_nodes, D, mode, dP, lddp, as_stream(stream))) {
+    GTS_LAUNCH_CHECK();
+    return GTS_OK;
+  }
   segsum_bwd_kernel<<<seg_grid(n_nodes), kSegThreads, 0, as_stream(stream)>>>(dOut, ldd, csc_indptr, csc_indices, in_indptr,
                                                                                n_nodes, D, mode, dP, lddp);
   GTS_LAUNCH_CHECK();

@@ -135,3 +135,35 @@ def test_segmax_full_size_idempotence(cuda_dev):
     indptr, indices = (t.cpu().numpy() for t in bg.csr)
     r_n, r_a = sage_ref.segment_max_first_ref(P.cpu(), indptr, indices)
     assert torch.equal(n1.cpu(), r_n) and torch.equal(a1.cpu().long(), r_a)
+
+
+@pytest.mark.parametrize("D", [128, 256])
+@pytest.mark.parametrize("mode", ["sum", "mean", "gcn"])
+def test_segsum_wide_matches_scalar_and_fp64(cuda_dev, D, mode):
+    """The vectorised sum/mean/gcn aggregation (forward over the in-edge CSR, backward over the out-edge CSC) against
+    an fp64 index_add restatement, on a graph with isolated nodes and a 40-neighbour hub."""
+    import numpy as np
+    from gnn_tumor_seg_b200 import graph as G, ops
+    rng = np.random.default_rng(11)
+    N = 3000
+    src = rng.integers(0, N - 5, size=40000); dst = rng.integers(0, N - 5, size=40000)        # last 5 nodes isolated
+    src = np.concatenate([src, rng.integers(0, N - 5, size=40)]); dst = np.concatenate([dst, np.full(40, 7)])
+    g = G.from_edge_list(src, dst, N).to(cuda_dev)
+    X = torch.randn(N, D, generator=torch.Generator().manual_seed(D))
+    s, d = torch.as_tensor(src), torch.as_tensor(dst)
+    deg = torch.bincount(d, minlength=N).double().view(-1, 1)
+    summed = torch.zeros(N, D, dtype=torch.float64).index_add(0, d, X.double()[s])
+    ref = {"sum": summed, "mean": torch.where(deg > 0, summed / deg.clamp(min=1), torch.zeros_like(summed)),
+           "gcn": (summed + X.double()) / (deg + 1)}[mode]
+    indptr, indices = g.csr
+    out = ops.segsum_fwd(X.to(cuda_dev), indptr, indices, mode)
+    assert (out.cpu().double() - ref).abs().max() < 1e-5 * max(1.0, ref.abs().max())
+    # backward = transpose of the forward operator: <out_bar, A x> == <A^T out_bar, x>
+    cptr, cidx, _ = g.csc
+    Gr = torch.randn(N, D, generator=torch.Generator().manual_seed(1))
+    dX = ops.segsum_bwd(Gr.to(cuda_dev), cptr, cidx, indptr, mode)
+    sc = {"sum": torch.ones_like(deg), "mean": torch.where(deg > 0, 1 / deg.clamp(min=1), torch.zeros_like(deg)), "gcn": 1 / (deg + 1)}[mode]
+    refb = torch.zeros(N, D, dtype=torch.float64).index_add(0, s, (Gr.double() * sc)[d])
+    if mode == "gcn":
+        refb = refb + Gr.double() * sc
+    assert (dX.cpu().double() - refb).abs().max() < 1e-5 * max(1.0, refb.abs().max())

@@ -166,11 +166,12 @@ def test_inference_no_grad_and_eval_argmax_agreement(cuda_dev):
     assert agree >= 0.9999
 
 
+@pytest.mark.parametrize("sizes", [[64, 32], [256, 128]])      # [256, 128]: the wide (vectorised) aggregation kernels
 @pytest.mark.parametrize("agg", ["mean", "gcn"])
-def test_graphsage_mean_gcn(cuda_dev, agg):
+def test_graphsage_mean_gcn(cuda_dev, agg, sizes):
     bg, feats, labels, csr, (s, d) = _batch([3, 4], isolated=2)
     torch.manual_seed(3)
-    net = networks.GraphSage(20, [64, 32], 4, agg, 0).to(cuda_dev)
+    net = networks.GraphSage(20, sizes, 4, agg, 0).to(cuda_dev)
     x = feats.to(cuda_dev).requires_grad_(True)
     out = net(bg.to(cuda_dev), x)
     out.square().sum().backward()
