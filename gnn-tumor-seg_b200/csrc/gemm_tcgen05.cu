@@ -1071,7 +1071,7 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_remote(ready_leader + (uint32_t)slot * 8);
+        if (lane == 0) { if (rank == 0) mbar_arrive(&ready[slot]); else mbar_arrive_remote(ready_leader + (uint32_t)slot * 8); }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
         if (++slot == A_SLOTS) { slot = 0; sphase ^= 1; }
       }
@@ -1112,7 +1112,7 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         // the ready barrier is per A slot: do not arrive for round i before the phase of round i - A_SLOTS is over
         mbar_wait(&a_free[slot], sphase ^ 1);
         __syncwarp();
-        if (lane == 0) mbar_arrive_remote(ready_leader + (uint32_t)slot * 8);
+        if (lane == 0) { if (rank == 0) mbar_arrive(&ready[slot]); else mbar_arrive_remote(ready_leader + (uint32_t)slot * 8); }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
         if (++slot == A_SLOTS) { slot = 0; sphase ^= 1; }
       }
@@ -1139,7 +1139,7 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         epilogue_tile<TN>(p, t_base + L::BN_MAX, m0, n0, Cout + p.c2_off, stg, lane, 0, 32, false, &tmem_full[acc], full_phase);
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(tmem_empty_leader + (uint32_t)acc * 8);
+      if (lane == 0) { if (rank == 0) mbar_arrive(&tmem_empty[acc]); else mbar_arrive_remote(tmem_empty_leader + (uint32_t)acc * 8); }
     }
   }
 
