@@ -360,7 +360,7 @@ def run_ours(args):
                              "peak_note": "TF32 dense peak taken as 1/2 of the measured sustained bf16 cuBLAS figure"},
     }
     ncu = load_ncu_traffic()
-    kern["segmax_fwd"]["traffic"] = traffic_of(ncu, "segmax_fwd_wide")
+    kern["segmax_fwd"]["traffic"] = traffic_of(ncu, "segmax_fwd_pipe")
     kern["segmax_bwd"]["traffic"] = traffic_of(ncu, "segmax_bwd_vec")
     kern["gemm_concat_k512"]["traffic"] = traffic_of(ncu, "gemm_x3ts2_kernel<0") if args.mode == "tf32x3" else None
     tot = sum(v["ms"] for v in breakdown.values()) or 1.0

@@ -11,6 +11,7 @@
 // (bit-exact arg-max vs the oracle).  HBM-bound: algorithmic bytes
 // 4*(N*D read + N*D write + N*D argmax + (N+1) + E).
 #include "common.cuh"
+#include <algorithm>
 #include <cfloat>
 #include <cstdlib>
 
@@ -32,6 +33,32 @@ __device__ __forceinline__ void fold_one(float& best, int& arg, float v, int u, 
       "@p fma.rn.f32 %0, %2, %4, %5;\n\t"
       "@p mad.lo.s32 %1, %1, %6, %3;\n\t}"
       : "+f"(best), "+r"(arg) : "f"(v), "r"(u), "f"(k.one), "f"(k.neg_zero), "r"(k.zero));
+}
+// Select forms for the double-buffered kernel (template parameter FV): 0 = the FFMA / IMAD form above;
+// 3 = FADD / IMAD: v + (-0.0f) == v exactly for every v, and its one opaque operand comes straight from the constant
+// bank, so the two float constants need no registers.  (Rejected by SASS inspection: plain predicated movs become
+// FSEL + SEL, both ALU pipe; `u * 1 + 0` is hoisted out of the column loop as a common subexpression and the select
+// comes back as an ALU-pipe SEL.)
+template <int FV>
+__device__ __forceinline__ void fold_one_p(float& best, int& arg, float v, int u, const FoldConst& k) {
+  if (FV == 0) {
+    fold_one(best, arg, v, u, k);
+  } else {
+    // ONE opaque register z (bits 0: +0.0f and int 0) serves both selects: v - (+0.0f) == v exactly for every v
+    // (incl. -0.0f, infinities, denormals; the negation is an operand modifier) and arg * 0 + u == u
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.gt.f32 p, %2, %0;\n\t"
+        "@p sub.rn.f32 %0, %2, %4;\n\t"
+        "@p mad.lo.s32 %1, %1, %5, %3;\n\t}"
+        : "+f"(best), "+r"(arg) : "f"(v), "r"(u), "f"(__int_as_float(k.zero)), "r"(k.zero));
+  }
+}
+template <int FV>
+__device__ __forceinline__ void fold_max_p(float4& best, int4& arg, const float4& v, int u, const FoldConst& k) {
+  fold_one_p<FV>(best.x, arg.x, v.x, u, k);
+  fold_one_p<FV>(best.y, arg.y, v.y, u, k);
+  fold_one_p<FV>(best.z, arg.z, v.z, u, k);
+  fold_one_p<FV>(best.w, arg.w, v.w, u, k);
 }
 // inference (no arg-max wanted): the value alone is one FMNMX per element
 __device__ __forceinline__ void fold_val(float4& best, const float4& v) {
@@ -149,8 +176,6 @@ segmax_fwd_wide_kernel(const float* __restrict__ P, int64_t ldp, const int32_t* 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const unsigned full = 0xffffffffu;
-  const int64_t v_begin = (int64_t)blockIdx.x * nodes_per_cta;
-  const int64_t v_end = v_begin + nodes_per_cta < N ? v_begin + nodes_per_cta : N;
   const int slab4 = blockIdx.y * 32 * VEC;       // gridDim.y column slabs of 128*VEC floats each
   const char* __restrict__ Pl = reinterpret_cast<const char*>(reinterpret_cast<const float4*>(P) + slab4 + lane);
   const uint32_t ld_bytes = (uint32_t)(ldp << 2);   // host guarantees N * ldp * 4 < 2^32: one IMAD.WIDE per row address
@@ -158,6 +183,9 @@ segmax_fwd_wide_kernel(const float* __restrict__ P, int64_t ldp, const int32_t* 
     return reinterpret_cast<const float4*>(Pl + (uint64_t)(uint32_t)u * ld_bytes);
   };
 
+  // sweep: chunk blockIdx.x + s * gridDim.x at step s (one step when nodes_per_cta = ceil(N / grid))
+  for (int64_t v_begin = (int64_t)blockIdx.x * nodes_per_cta; v_begin < N; v_begin += (int64_t)gridDim.x * nodes_per_cta) {
+  const int64_t v_end = v_begin + nodes_per_cta < N ? v_begin + nodes_per_cta : N;
   for (int64_t v = v_begin + warp; v < v_end; v += kWideWarps) {
     const int32_t beg = indptr[v], end = indptr[v + 1];
     float4 best[VEC];
@@ -205,6 +233,7 @@ segmax_fwd_wide_kernel(const float* __restrict__ P, int64_t ldp, const int32_t* 
       if (WRITE_ARG) stg_na(reinterpret_cast<int4*>(argmax + v * ldarg) + slab4 + lane + 32 * c, arg[c]);
     }
   }
+  }
 }
 
 template <int VEC, int kWideWarps>
@@ -212,12 +241,223 @@ static int launch_fwd_wide(const float* P, int64_t ldp, const int32_t* indptr, c
                            float* neigh, int64_t ldn, int32_t* argmax, int64_t ldarg, cudaStream_t st, int slabs = 1) {
   // one CTA per SM, contiguous id ranges of (almost) equal length
   int64_t grid = sm_count();
-  const int64_t per_cta = ceil_div<int64_t>(N, grid);
-  grid = ceil_div<int64_t>(N, per_cta);
+  static const int chunk_req = getenv("GTS_SEGMAX_CHUNK") ? atoi(getenv("GTS_SEGMAX_CHUNK")) : 0;
+  const int64_t per_cta = chunk_req > 0 ? chunk_req : ceil_div<int64_t>(N, grid);
+  grid = std::min<int64_t>(grid, ceil_div<int64_t>(N, per_cta));
   if (argmax)
     segmax_fwd_wide_kernel<VEC, true, kWideWarps><<<dim3((unsigned)grid, slabs), kWideWarps * 32, 0, st>>>(P, ldp, indptr, indices, N, neigh, ldn, argmax, ldarg, per_cta, fold_const());
   else
     segmax_fwd_wide_kernel<VEC, false, kWideWarps><<<dim3((unsigned)grid, slabs), kWideWarps * 32, 0, st>>>(P, ldp, indptr, indices, N, neigh, ldn, nullptr, 0, per_cta, fold_const());
+  GTS_LAUNCH_CHECK();
+  return GTS_OK;
+}
+
+// Second form of the wide kernel: software-pipelined.  What the measurements said about the first one
+// (profiles/r01_segmax_variants.md): it is neither purely issue-bound nor DRAM-bound - a warp loads four rows, waits
+// for the slowest of them (almost every group holds a +-z neighbour row that misses L1) and only then folds, so time
+// goes with the number of resident warps; and every row is fetched from DRAM about twice because the CTAs that share
+// it (one z-slab of ids apart) touch it a whole kernel duration apart.  This form changes four things:
+//   * stages of R rows are double-buffered (ping-pong A / C): the loads of the next stage are in flight while the
+//     current one is folded, so a warp never drains its memory pipeline inside a row.  R = 1 needs 16 row registers
+//     (32 resident warps in 64 registers), R = 2 needs 32 (24 warps in 80);
+//   * the row's first neighbour INITIALISES (best, arg) instead of being folded into (-inf, -1) (inputs are finite:
+//     P is a ReLU output; a row of -inf/NaN would differ from the fold form), and tails are exact: the head takes
+//     1..2R rows so that whole double-stages remain - no padded repeats of the last neighbour;
+//   * the next node's (beg, end) and neighbour ids are fetched while the current node is processed, which takes
+//     the indptr -> indices -> row dependent-latency chain off the per-node critical path;
+//   * the two selects share ONE opaque zero register (fold_one_p) instead of two float constants and an int;
+//   * the id space is swept by all CTAs side by side in short pieces (see the iterator below) instead of one long
+//     contiguous range per CTA, which keeps the shared rows in L2.
+// Rows with more than 32 in-edges take the plain loop at the end (never on supervoxel RAGs: max degree ~30).
+// Tried and dropped: prefetch.global.L2 of the next node's rows (+1.4 GB of L2 requests for lines that mostly hit L1
+// anyway: 92 -> 111 us).
+constexpr int kMaxPieceSteps = 512;
+
+template <int VEC, bool WRITE_ARG, int kWarps, int FV, int R>
+__global__ void __launch_bounds__(kWarps * 32, 1)
+segmax_fwd_pipe_kernel(const float* __restrict__ P, int64_t ldp, const int32_t* __restrict__ indptr,
+                       const int32_t* __restrict__ indices, int32_t N,
+                       float* __restrict__ neigh, int64_t ldn, int32_t* __restrict__ argmax, int64_t ldarg,
+                       int32_t steps, const FoldConst fc) {
+  constexpr int G = 2 * R;      // rows per loop iteration (two stages)
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const unsigned full = 0xffffffffu;
+  // piece table.  The id space is cut into steps * gridDim.x nearly equal pieces; at sweep step s the CTA owns piece
+  // s * gridDim.x + blockIdx.x and its warps walk the concatenation of its pieces kWarps apart (equal node counts
+  // per warp and per CTA, +-1).  steps = 1 is one contiguous range per CTA; with short pieces the rows a CTA shares
+  // with its neighbours in id space are touched by everybody at about the same time (L2 hits), while neighbours
+  // within a piece still hit L1.
+  __shared__ int32_t s_lo[kMaxPieceSteps + 1], s_len[kMaxPieceSteps + 1];
+  {
+    const int64_t n_pieces = (int64_t)steps * gridDim.x;
+    for (int32_t t = threadIdx.x; t < steps; t += kWarps * 32) {
+      const int64_t k = (int64_t)t * gridDim.x + blockIdx.x;
+      const int32_t lo = (int32_t)(k * N / n_pieces);
+      s_lo[t] = lo;
+      s_len[t] = (int32_t)((k + 1) * N / n_pieces) - lo;
+    }
+    if (threadIdx.x == 0) { s_lo[steps] = N; s_len[steps] = 0x7fffffff; }     // sentinel: the iterator parks on N
+    __syncthreads();
+  }
+  int32_t it_s = 0, it_off = warp;
+  auto next_node = [&]() {
+    int32_t len = s_len[it_s];
+    while (it_off >= len) { it_off -= len; len = s_len[++it_s]; }
+    const int32_t r = s_lo[it_s] + it_off;
+    if (it_s < steps) it_off += kWarps; else it_off = 0;
+    return r;             // == N once exhausted
+  };
+
+  const int slab4 = blockIdx.y * 32 * VEC;       // gridDim.y column slabs of 128 * VEC floats each
+  const char* __restrict__ Pl = reinterpret_cast<const char*>(reinterpret_cast<const float4*>(P) + slab4 + lane);
+  const uint32_t ld_bytes = (uint32_t)(ldp << 2);   // host guarantees N * ldp * 4 < 2^32
+  struct Row { float4 c[VEC]; };
+  auto row_ptr = [&](int32_t u) {
+    uint64_t a;      // base + u * ld_bytes
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(u), "r"(ld_bytes), "l"(Pl));
+    return reinterpret_cast<const float4*>(a);
+  };
+  auto load_row = [&](Row& r, int32_t u) {
+    const float4* p = row_ptr(u);
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) r.c[c] = ldg_nc(p + 32 * c);
+  };
+  // predicated form (registers keep their contents when !on): keeps the stage loop free of branches
+  auto load_row_if = [&](Row& r, int32_t u, int32_t on) {
+    const float4* p = row_ptr(u);
+#pragma unroll
+    for (int c = 0; c < VEC; ++c)
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t"
+                   "@p ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
+                   : "+f"(r.c[c].x), "+f"(r.c[c].y), "+f"(r.c[c].z), "+f"(r.c[c].w) : "l"(p + 32 * c), "r"(on));
+  };
+#define FOLD_ROW(ROW, U)                                                                                         \
+  _Pragma("unroll") for (int c_ = 0; c_ < VEC; ++c_) {                                                           \
+    if (WRITE_ARG) fold_max_p<FV>(best[c_], arg[c_], (ROW).c[c_], (U), fc); else fold_val(best[c_], (ROW).c[c_]); \
+  }
+
+  int32_t v = next_node();
+  if (v >= N) return;
+  // software pipeline over nodes: the next node's (beg, end) are requested when the current node starts and its
+  // neighbour ids once the head rows are folded (the offsets have arrived by then)
+  int32_t beg = indptr[v], end = indptr[v + 1];
+  int32_t my_idx = (beg + lane < end) ? indices[beg + lane] : 0;
+
+  while (v < N) {
+    const int32_t deg = end - beg;
+    const int32_t v1 = next_node();
+    int32_t nbeg = 0, nend = 0, n_idx = 0;
+    if (v1 < N) { nbeg = indptr[v1]; nend = indptr[v1 + 1]; }
+
+    float4 best[VEC];
+    int4 arg[VEC];
+    if (deg > 0 && deg <= 32) {
+      // head: 1..G rows so that a multiple of G remains; the first one initialises (best, arg)
+      const int32_t head = ((deg - 1) & (G - 1)) + 1;
+      Row A[R], C[R];
+      int32_t ua[R], uc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) A[r].c[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ua[r] = 0; uc[r] = 0;
+      }
+      const int32_t u0 = __shfl_sync(full, my_idx, 0);
+      {
+        Row F;
+        load_row(F, u0);
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) { best[c] = F.c[c]; arg[c] = make_int4(u0, u0, u0, u0); }
+      }
+      // head rows 1 .. head-1 (at most G-1 = 2R-1) are staged in C[0..R-1] then A[0..R-2]
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (head >= 2 + r) { uc[r] = __shfl_sync(full, my_idx, 1 + r); load_row(C[r], uc[r]); }
+#pragma unroll
+      for (int r = 0; r < R - 1; ++r)
+        if (head >= 2 + R + r) { ua[r] = __shfl_sync(full, my_idx, 1 + R + r); load_row(A[r], ua[r]); }
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (head >= 2 + r) FOLD_ROW(C[r], uc[r]);
+#pragma unroll
+      for (int r = 0; r < R - 1; ++r)
+        if (head >= 2 + R + r) FOLD_ROW(A[r], ua[r]);
+      int32_t j = head;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        ua[r] = __shfl_sync(full, my_idx, j + r);      // lane index wraps mod 32
+        load_row_if(A[r], ua[r], j < deg);
+      }
+      if (nbeg + lane < nend) n_idx = indices[nbeg + lane];
+      // whole double-stages from here: A holds neighbours j .. j+R-1 on entry
+      while (j < deg) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) { uc[r] = __shfl_sync(full, my_idx, j + R + r); load_row(C[r], uc[r]); }
+#pragma unroll
+        for (int r = 0; r < R; ++r) FOLD_ROW(A[r], ua[r]);
+        j += G;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          ua[r] = __shfl_sync(full, my_idx, j + r);
+          load_row_if(A[r], ua[r], j < deg);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) FOLD_ROW(C[r], uc[r]);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) {
+        best[c] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        arg[c] = make_int4(-1, -1, -1, -1);
+      }
+      if (nbeg + lane < nend) n_idx = indices[nbeg + lane];
+      for (int32_t e = beg; e < end; ++e) {      // deg > 32: plain loop, ids by warp-uniform loads
+        const int32_t u = indices[e];
+        Row T;
+        load_row(T, u);
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+          if (WRITE_ARG) fold_max(best[c], arg[c], T.c[c], u, fc); else fold_val(best[c], T.c[c]);
+        }
+      }
+      if (deg == 0) {                            // no in-edges: DGL fills 0
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) best[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+      stg_na(reinterpret_cast<float4*>(neigh + (int64_t)v * ldn) + slab4 + lane + 32 * c, best[c]);
+      if (WRITE_ARG) stg_na(reinterpret_cast<int4*>(argmax + (int64_t)v * ldarg) + slab4 + lane + 32 * c, arg[c]);
+    }
+    v = v1;
+    beg = nbeg; end = nend; my_idx = n_idx;
+  }
+#undef FOLD_ROW
+}
+
+template <int VEC, int kWarps, int FV, int R>
+static int launch_fwd_pipe(const float* P, int64_t ldp, const int32_t* indptr, const int32_t* indices, int32_t N,
+                           float* neigh, int64_t ldn, int32_t* argmax, int64_t ldarg, cudaStream_t st, int piece_req,
+                           int slabs = 1) {
+  // piece_req = target nodes per piece (0: one contiguous range per CTA)
+  const int64_t grid = std::min<int64_t>(sm_count(), ceil_div<int64_t>(N, kWarps));
+  int64_t steps = 1;
+  if (piece_req > 0) steps = std::min<int64_t>(kMaxPieceSteps, std::max<int64_t>(1, (N + grid * piece_req / 2) / (grid * piece_req)));
+  static const bool max_l1 = [] {     // the gathers live on L1 hits: ask for the largest L1 carve-out (A/B: GTS_SEGMAX_MAXL1=0)
+    const bool on = !(getenv("GTS_SEGMAX_MAXL1") && atoi(getenv("GTS_SEGMAX_MAXL1")) == 0);
+    if (on) {
+      cudaFuncSetAttribute(segmax_fwd_pipe_kernel<VEC, true, kWarps, FV, R>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+      cudaFuncSetAttribute(segmax_fwd_pipe_kernel<VEC, false, kWarps, FV, R>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    }
+    return on;
+  }();
+  (void)max_l1;
+  if (argmax)
+    segmax_fwd_pipe_kernel<VEC, true, kWarps, FV, R><<<dim3((unsigned)grid, slabs), kWarps * 32, 0, st>>>(P, ldp, indptr, indices, N, neigh, ldn, argmax, ldarg, (int32_t)steps, fold_const());
+  else
+    segmax_fwd_pipe_kernel<VEC, false, kWarps, FV, R><<<dim3((unsigned)grid, slabs), kWarps * 32, 0, st>>>(P, ldp, indptr, indices, N, neigh, ldn, nullptr, 0, (int32_t)steps, fold_const());
   GTS_LAUNCH_CHECK();
   return GTS_OK;
 }
@@ -565,6 +805,29 @@ int gts_segmax_fwd(const float* P, int64_t ldp, const int32_t* indptr, const int
   static const int wide_warps = getenv("GTS_SEGMAX_WARPS") ? atoi(getenv("GTS_SEGMAX_WARPS")) : 32;
   const bool wide_ok = !no_wide && vec_ok && (int64_t)n_nodes * ldp * 4 < ((int64_t)1 << 32);
   if (wide_ok && D == 128) return launch_fwd_wide<1, 32>(P, ldp, indptr, indices, n_nodes, neigh, ldn, argmax, ldarg, st);
+  // D == 256 (the hidden layers): the software-pipelined form (segmax_fwd_pipe_kernel), 32 warps, one row per stage,
+  // sweep pieces of ~64 nodes - the fastest of the measured matrix (profiles/r01_segmax_variants.md).  A/B switches:
+  // GTS_SEGMAX_PIPE=<warps> (0 = the grouped form), GTS_SEGMAX_STAGE=<rows per stage>, GTS_SEGMAX_FOLD=<0|3>,
+  // GTS_SEGMAX_CHUNK=<nodes per sweep piece; 0 = one contiguous range per CTA>, GTS_SEGMAX_SLABS=2, GTS_SEGMAX_MAXL1=0.
+  static const int pipe_warps = getenv("GTS_SEGMAX_PIPE") ? atoi(getenv("GTS_SEGMAX_PIPE")) : 32;
+  static const int seg_chunk = getenv("GTS_SEGMAX_CHUNK") ? atoi(getenv("GTS_SEGMAX_CHUNK")) : (pipe_warps > 0 ? 64 : 0);
+  static const int pipe_fold = getenv("GTS_SEGMAX_FOLD") ? atoi(getenv("GTS_SEGMAX_FOLD")) : 3;
+  static const int pipe_stage = getenv("GTS_SEGMAX_STAGE") ? atoi(getenv("GTS_SEGMAX_STAGE")) : 1;
+  if (wide_ok && D == 256 && pipe_warps > 0) {
+#define GTS_PIPE(W, F, S)                                                                            \
+    if (pipe_warps == W && pipe_fold == F && pipe_stage == S)                                         \
+      return launch_fwd_pipe<2, W, F, S>(P, ldp, indptr, indices, n_nodes, neigh, ldn, argmax, ldarg, st, seg_chunk);
+    static const int pipe_slabs = getenv("GTS_SEGMAX_SLABS") ? atoi(getenv("GTS_SEGMAX_SLABS")) : 1;
+    if (pipe_slabs == 2) {     // two 128-column slabs, one CTA each: half the L1 working set per SM
+      if (pipe_stage == 1) return launch_fwd_pipe<1, 32, 3, 1>(P, ldp, indptr, indices, n_nodes, neigh, ldn, argmax, ldarg, st, seg_chunk, 2);
+      if (pipe_stage == 2) return launch_fwd_pipe<1, 32, 3, 2>(P, ldp, indptr, indices, n_nodes, neigh, ldn, argmax, ldarg, st, seg_chunk, 2);
+      return launch_fwd_pipe<1, 32, 3, 4>(P, ldp, indptr, indices, n_nodes, neigh, ldn, argmax, ldarg, st, seg_chunk, 2);
+    }
+    GTS_PIPE(20, 3, 2) GTS_PIPE(24, 3, 2) GTS_PIPE(24, 0, 2)
+    GTS_PIPE(24, 3, 1) GTS_PIPE(28, 3, 1) GTS_PIPE(32, 3, 1) GTS_PIPE(32, 0, 1)
+#undef GTS_PIPE
+    GTS_CHECK_ARG(false, "gts_segmax_fwd: unsupported GTS_SEGMAX_PIPE / _FOLD / _STAGE combination");
+  }
   if (wide_ok && D == 256) {
     if (wide_warps == 48) return launch_fwd_wide<1, 24>(P, ldp, indptr, indices, n_nodes, neigh, ldn, argmax, ldarg, st, 2);
     if (wide_warps == 64) return launch_fwd_wide<1, 32>(P, ldp, indptr, indices, n_nodes, neigh, ldn, argmax, ldarg, st, 2);
