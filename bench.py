@@ -297,6 +297,10 @@ def run_ours(args):
     loss_val = float(loss)
 
     # ---- end to end from pinned host buffers through the public API ----
+    # every step: H2D of the step's edge lists / features / labels from pinned memory + device CSR build, forward, loss,
+    # backward, D2H loss (host sync per step, as the reference's loss.item()).  In-stream on purpose: staging batch i+1
+    # through data_loader.DevicePrefetcher before step i is enqueued was measured SLOWER here (5.61 vs 5.49 ms: with a
+    # sync per step the host-side staging delays the first kernel of the step by as much as the overlap saves).
     def e2e_step(i):
         bg, f, l = pinned[i % len(pinned)]
         dg = bg.to(dev)                                    # H2D edge lists + device CSR build
@@ -487,24 +491,35 @@ def run_infer(args):
     resident = [(hg.to(dev), f.to(dev), [s_.to(dev) for s_ in svs], [project.crop_inverse_maps(c, device=dev) for c in crops], offs)
                 for hg, f, svs, crops, offs in host]
     vol = torch.empty(project.BRATS_SHAPE, dtype=torch.int16, device=dev)
-    vol_host = torch.empty(project.BRATS_SHAPE, dtype=torch.int16).pin_memory()
     my_groups = [my_ids[i:i + B] for i in range(0, len(my_ids), B)]          # the last group may be short
+    from gnn_tumor_seg_b200.data_loader import DevicePrefetcher
+    downloader = project.VolumeDownloader(depth=4, device=dev)
 
-    def one(gi, n_in_group, e2e):
-        k = gi % n_groups
-        if e2e:
-            hg, f, svs, crops, offs = host[k]
-            dg, fd = hg.to(dev), f.to(dev, non_blocking=True)
-            svs_d = [s_.to(dev, non_blocking=True) for s_ in svs[:n_in_group]]
-            invs = resident[k][3]
-        else:
-            dg, fd, svs_d, invs, offs = resident[k]
+    def forward_project(dg, fd, svs_d, invs, offs, n_in_group, e2e):
         with torch.no_grad():
             logits = net(dg, fd)
         for j in range(n_in_group):
-            project.project_labels_to_brats(logits[int(offs[j]):int(offs[j + 1])], svs_d[j], None, out=vol, inv_maps=invs[j])
+            if e2e:      # label volume -> pinned host buffer on the copy stream, overlapped with the next graph
+                slot, out = downloader.acquire()
+            else:
+                out = vol
+            project.project_labels_to_brats(logits[int(offs[j]):int(offs[j + 1])], svs_d[j], None, out=out, inv_maps=invs[j])
             if e2e:
-                vol_host.copy_(vol, non_blocking=True)
+                downloader.submit(slot)
+
+    def run_groups(e2e, groups):
+        if not e2e:
+            for gi, grp in enumerate(groups):
+                dg, fd, svs_d, invs, offs = resident[gi % n_groups]
+                forward_project(dg, fd, svs_d, invs, offs, len(grp), False)
+            return
+        # e2e: graph / features / supervoxel maps from pinned host memory, staged one group ahead on a side stream
+        src = ((host[gi % n_groups][0], host[gi % n_groups][1], tuple(host[gi % n_groups][2][:len(grp)]))
+               for gi, grp in enumerate(groups))
+        for gi, (dg, fd, svs_d) in enumerate(DevicePrefetcher(src, dev)):
+            k = gi % n_groups
+            forward_project(dg, fd, svs_d, resident[k][3], host[k][4], len(groups[gi]), True)
+        downloader.drain()
 
     def barrier():
         if world > 1:
@@ -512,14 +527,12 @@ def run_infer(args):
         torch.cuda.synchronize()
 
     def timed(e2e, steps):
-        for gi, grp in enumerate(my_groups[:6]):
-            one(gi, len(grp), e2e)
+        run_groups(e2e, my_groups[:6])
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            for gi, grp in enumerate(my_groups):
-                one(gi, len(grp), e2e)
+            run_groups(e2e, my_groups)          # e2e: ends with downloader.drain(), so every volume is on the host
         e1.record()
         barrier()
         return e0.elapsed_time(e1) / steps

@@ -114,15 +114,23 @@ gat_fwd_kernel(const float* __restrict__ Z, int64_t ldz, const float* __restrict
                const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, int64_t NH, int H, int F,
                float slope, const float* __restrict__ res, int64_t ldres, const float* __restrict__ bias, int act,
                float* __restrict__ out, int64_t ldo, float* __restrict__ rowmax, float* __restrict__ rowsum,
-               int32_t* __restrict__ err) {
+               int32_t* __restrict__ err, int sweep_piece) {
   const int lane = threadIdx.x & 31;
   // RANGE: one 1024-thread CTA per SM owns a contiguous node range and walks it HEAD-MAJOR (all 32 warps on the same
   // head of 32 consecutive nodes): consecutive supervoxels share most of their neighbours, so the 1 KB head slices of
   // the neighbour rows are re-read from L1 (node-major order keeps 8 nodes x 4 heads x 15 rows in flight and thrashes it)
+  // The id space is swept in `steps` rounds of gridDim.x nearly equal pieces (piece s * gridDim.x + blockIdx.x at
+  // round s) instead of one long range per CTA: the neighbour rows a CTA shares with the CTAs next to it in id space
+  // (the +-z supervoxels, one z-slab of ids away) are then touched by everybody at about the same time and come from
+  // L2 instead of DRAM (see segmax.cu / profiles/r01_segmax_variants.md).  sweep_piece = target nodes per piece.
   const int64_t n_total = NH / H;
-  const int64_t per_cta = RANGE ? (n_total + gridDim.x - 1) / gridDim.x : 0;
-  const int64_t r_beg = RANGE ? (int64_t)blockIdx.x * per_cta : 0;
-  const int64_t r_cnt = RANGE ? max((int64_t)0, min(n_total, r_beg + per_cta) - r_beg) : 0;
+  const int64_t steps = (RANGE && sweep_piece > 0)
+      ? max((int64_t)1, (n_total + (int64_t)gridDim.x * sweep_piece / 2) / ((int64_t)gridDim.x * sweep_piece)) : 1;
+  const int64_t n_pieces = steps * gridDim.x;
+  for (int64_t sweep = 0; sweep < steps; ++sweep) {
+  const int64_t piece = sweep * gridDim.x + blockIdx.x;
+  const int64_t r_beg = RANGE ? piece * n_total / n_pieces : 0;
+  const int64_t r_cnt = RANGE ? (piece + 1) * n_total / n_pieces - r_beg : 0;
   const int64_t i_beg = RANGE ? (int64_t)(threadIdx.x >> 5) : ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
   const int64_t i_end = RANGE ? r_cnt * H : NH;
   const int64_t i_step = RANGE ? (int64_t)(blockDim.x >> 5) : (((int64_t)gridDim.x * blockDim.x) >> 5);
@@ -183,6 +191,7 @@ gat_fwd_kernel(const float* __restrict__ Z, int64_t ldz, const float* __restrict
     acc.store(out + v * ldo + (int64_t)h * F, F, lane);
     if (lane == 0) { rowmax[w] = m; rowsum[w] = l; }
   }
+  }
 }
 
 __global__ void gat_act_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, int64_t n, int act,
@@ -205,15 +214,23 @@ gat_bwd_dst_kernel(const float* __restrict__ Z, int64_t ldz, const float* __rest
                    const float* __restrict__ rowmax, const float* __restrict__ rowsum,
                    const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                    const float* __restrict__ dO, int64_t lddo, int64_t NH, int H, int F, float slope,
-                   float* __restrict__ dt_edge, float* __restrict__ der) {
+                   float* __restrict__ dt_edge, float* __restrict__ der, int sweep_piece) {
   const int lane = threadIdx.x & 31;
   // RANGE: one 1024-thread CTA per SM owns a contiguous node range and walks it HEAD-MAJOR (all 32 warps on the same
   // head of 32 consecutive nodes): consecutive supervoxels share most of their neighbours, so the 1 KB head slices of
   // the neighbour rows are re-read from L1 (node-major order keeps 8 nodes x 4 heads x 15 rows in flight and thrashes it)
+  // The id space is swept in `steps` rounds of gridDim.x nearly equal pieces (piece s * gridDim.x + blockIdx.x at
+  // round s) instead of one long range per CTA: the neighbour rows a CTA shares with the CTAs next to it in id space
+  // (the +-z supervoxels, one z-slab of ids away) are then touched by everybody at about the same time and come from
+  // L2 instead of DRAM (see segmax.cu / profiles/r01_segmax_variants.md).  sweep_piece = target nodes per piece.
   const int64_t n_total = NH / H;
-  const int64_t per_cta = RANGE ? (n_total + gridDim.x - 1) / gridDim.x : 0;
-  const int64_t r_beg = RANGE ? (int64_t)blockIdx.x * per_cta : 0;
-  const int64_t r_cnt = RANGE ? max((int64_t)0, min(n_total, r_beg + per_cta) - r_beg) : 0;
+  const int64_t steps = (RANGE && sweep_piece > 0)
+      ? max((int64_t)1, (n_total + (int64_t)gridDim.x * sweep_piece / 2) / ((int64_t)gridDim.x * sweep_piece)) : 1;
+  const int64_t n_pieces = steps * gridDim.x;
+  for (int64_t sweep = 0; sweep < steps; ++sweep) {
+  const int64_t piece = sweep * gridDim.x + blockIdx.x;
+  const int64_t r_beg = RANGE ? piece * n_total / n_pieces : 0;
+  const int64_t r_cnt = RANGE ? (piece + 1) * n_total / n_pieces - r_beg : 0;
   const int64_t i_beg = RANGE ? (int64_t)(threadIdx.x >> 5) : ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
   const int64_t i_end = RANGE ? r_cnt * H : NH;
   const int64_t i_step = RANGE ? (int64_t)(blockDim.x >> 5) : (((int64_t)gridDim.x * blockDim.x) >> 5);
@@ -264,6 +281,7 @@ gat_bwd_dst_kernel(const float* __restrict__ Z, int64_t ldz, const float* __rest
     der_part = warp_sum(der_part);
     if (lane == 0) der[w] = der_part;
   }
+  }
 }
 
 // Backward pass B, by source over the out-edge CSC.
@@ -274,15 +292,23 @@ gat_bwd_src_kernel(const float* __restrict__ el, const float* __restrict__ er, c
                    const int32_t* __restrict__ csc2csr, const float* __restrict__ dO, int64_t lddo,
                    const float* __restrict__ dt_edge, const float* __restrict__ der, const float* __restrict__ al,
                    const float* __restrict__ ar, int64_t NH, int H, int F, float slope,
-                   float* __restrict__ dZ, int64_t lddz, float* __restrict__ del) {
+                   float* __restrict__ dZ, int64_t lddz, float* __restrict__ del, int sweep_piece) {
   const int lane = threadIdx.x & 31;
   // RANGE: one 1024-thread CTA per SM owns a contiguous node range and walks it HEAD-MAJOR (all 32 warps on the same
   // head of 32 consecutive nodes): consecutive supervoxels share most of their neighbours, so the 1 KB head slices of
   // the neighbour rows are re-read from L1 (node-major order keeps 8 nodes x 4 heads x 15 rows in flight and thrashes it)
+  // The id space is swept in `steps` rounds of gridDim.x nearly equal pieces (piece s * gridDim.x + blockIdx.x at
+  // round s) instead of one long range per CTA: the neighbour rows a CTA shares with the CTAs next to it in id space
+  // (the +-z supervoxels, one z-slab of ids away) are then touched by everybody at about the same time and come from
+  // L2 instead of DRAM (see segmax.cu / profiles/r01_segmax_variants.md).  sweep_piece = target nodes per piece.
   const int64_t n_total = NH / H;
-  const int64_t per_cta = RANGE ? (n_total + gridDim.x - 1) / gridDim.x : 0;
-  const int64_t r_beg = RANGE ? (int64_t)blockIdx.x * per_cta : 0;
-  const int64_t r_cnt = RANGE ? max((int64_t)0, min(n_total, r_beg + per_cta) - r_beg) : 0;
+  const int64_t steps = (RANGE && sweep_piece > 0)
+      ? max((int64_t)1, (n_total + (int64_t)gridDim.x * sweep_piece / 2) / ((int64_t)gridDim.x * sweep_piece)) : 1;
+  const int64_t n_pieces = steps * gridDim.x;
+  for (int64_t sweep = 0; sweep < steps; ++sweep) {
+  const int64_t piece = sweep * gridDim.x + blockIdx.x;
+  const int64_t r_beg = RANGE ? piece * n_total / n_pieces : 0;
+  const int64_t r_cnt = RANGE ? (piece + 1) * n_total / n_pieces - r_beg : 0;
   const int64_t i_beg = RANGE ? (int64_t)(threadIdx.x >> 5) : ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
   const int64_t i_end = RANGE ? r_cnt * H : NH;
   const int64_t i_step = RANGE ? (int64_t)(blockDim.x >> 5) : (((int64_t)gridDim.x * blockDim.x) >> 5);
@@ -322,6 +348,7 @@ gat_bwd_src_kernel(const float* __restrict__ el, const float* __restrict__ er, c
     acc.fma(der[w], a);
     acc.store(dZ + u * lddz + (int64_t)h * F, F, lane);
     if (lane == 0) del[w] = del_u;
+  }
   }
 }
 
@@ -398,6 +425,11 @@ static inline int attn_blocks(int64_t N) {
   if (b < 1) b = 1;
   return (int)b;
 }
+// nodes per sweep piece of the RANGE kernels (A/B: GTS_GAT_PIECE; 0 = one contiguous range per CTA)
+static inline int gat_sweep_piece() {
+  static const int v = getenv("GTS_GAT_PIECE") ? atoi(getenv("GTS_GAT_PIECE")) : 256;   // measured: 18.3 (one range) -> 17.4 ms per GAT step
+  return v;
+}
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // Dispatch on (F, alignment): float4 lanes when possible.
@@ -457,7 +489,7 @@ int gts_gat_fwd(const float* Z, int64_t ldz, const float* el, const float* er,
   const bool vec_ok = (F % 4 == 0) && (ldz % 4 == 0) && (ldo % 4 == 0) && al16(Z) && al16(out) &&
                       (!res || ((ldres % 4 == 0) && al16(res))) && (!bias || al16(bias));
   GAT_DISPATCH(gat_fwd_kernel, vec_ok, F, Z, ldz, el, er, indptr, indices, NH, H, F, slope, res, ldres, bias, act,
-               out, ldo, rowmax, rowsum, err_flag);
+               out, ldo, rowmax, rowsum, err_flag, gat_sweep_piece());
   GTS_LAUNCH_CHECK();
   return GTS_OK;
 }
@@ -487,7 +519,7 @@ int gts_gat_bwd_dst(const float* Z, int64_t ldz, const float* el, const float* e
   const int64_t NH = (int64_t)n_nodes * H;
   const bool vec_ok = (F % 4 == 0) && (ldz % 4 == 0) && (lddo % 4 == 0) && al16(Z) && al16(dO);
   GAT_DISPATCH(gat_bwd_dst_kernel, vec_ok, F, Z, ldz, el, er, rowmax, rowsum, indptr, indices, dO, lddo, NH, H, F,
-               slope, dt_edge, der);
+               slope, dt_edge, der, gat_sweep_piece());
   GTS_LAUNCH_CHECK();
   return GTS_OK;
 }
@@ -506,7 +538,7 @@ int gts_gat_bwd_src(const float* el, const float* er, const float* rowmax, const
   const int64_t NH = (int64_t)n_nodes * H;
   const bool vec_ok = (F % 4 == 0) && (lddo % 4 == 0) && (lddz % 4 == 0) && al16(dO) && al16(dZ) && al16(attn_l) && al16(attn_r);
   GAT_DISPATCH(gat_bwd_src_kernel, vec_ok, F, el, er, rowmax, rowsum, csc_indptr, csc_indices, csc2csr, dO, lddo,
-               dt_edge, der, attn_l, attn_r, NH, H, F, slope, dZ, lddz, del);
+               dt_edge, der, attn_l, attn_r, NH, H, F, slope, dZ, lddz, del, gat_sweep_piece());
   GTS_LAUNCH_CHECK();
   return GTS_OK;
 }

@@ -115,3 +115,71 @@ class PredLogitDataset:
         crop_idxs = determine_tumor_crop(svs, node_logits)
         self.mri_crops[mri_id] = crop_idxs
         return crop_idxs
+
+
+class DevicePrefetcher:
+    """Stage batch i+1 on a side stream while batch i computes.
+
+    The reference moves every batch with ``.to(device)`` inside the step (model/gnn_model.py:38-40, DataLoader with
+    num_workers=0): host->device copies, and here the device CSR build, sit on the critical path of every step.
+    This iterator wraps any iterable of batches (tuples / lists whose members are ``BatchedGraph``s, tensors or
+    anything else, e.g. the ``(mri_ids, graph, features, labels)`` tuples of ``minibatch_graphs``): members are moved
+    with ``.to(device)`` on a private CUDA stream ``depth`` batches ahead (pinned host tensors make the copies
+    asynchronous), the consumer's stream waits on the staging event, and the allocator is told about the hand-over
+    (``record_stream``), so the yielded device objects can be used like the result of a plain ``.to(device)``.
+    """
+
+    def __init__(self, batches, device, depth=1):
+        if not torch.cuda.is_available():
+            raise GtsError("DevicePrefetcher needs a CUDA device (no CPU path)")
+        self.batches = batches
+        self.device = torch.device(device)
+        self.depth = max(1, int(depth))
+        self.stream = torch.cuda.Stream(device=self.device)
+
+    def __len__(self):
+        return len(self.batches)
+
+    def _stage(self, batch):
+        from .graph import BatchedGraph
+        with torch.cuda.stream(self.stream):
+            out = []
+            for m in (batch if isinstance(batch, (tuple, list)) else (batch,)):
+                if isinstance(m, BatchedGraph):
+                    out.append(m.to(self.device))
+                elif torch.is_tensor(m):
+                    out.append(m.to(self.device, non_blocking=True))
+                elif isinstance(m, (tuple, list)) and m and all(torch.is_tensor(t) for t in m):
+                    out.append(type(m)(t.to(self.device, non_blocking=True) for t in m))
+                else:
+                    out.append(m)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return (tuple(out) if isinstance(batch, (tuple, list)) else out[0]), ev
+
+    def _hand_over(self, staged, ev):
+        from .graph import BatchedGraph
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for m in (staged if isinstance(staged, tuple) else (staged,)):
+            if isinstance(m, BatchedGraph):
+                m.record_stream(cur)
+            elif torch.is_tensor(m) and m.is_cuda:
+                m.record_stream(cur)
+            elif isinstance(m, (tuple, list)):
+                for t in m:
+                    if torch.is_tensor(t) and t.is_cuda:
+                        t.record_stream(cur)
+        return staged
+
+    def __iter__(self):
+        from collections import deque
+        it = iter(self.batches)
+        q = deque()
+        for b in it:
+            q.append(self._stage(b))
+            if len(q) > self.depth:           # batch i+depth is staged before batch i is handed to the consumer
+                yield self._hand_over(*q.popleft())
+        while q:
+            yield self._hand_over(*q.popleft())
+

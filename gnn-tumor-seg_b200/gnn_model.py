@@ -15,6 +15,7 @@ from torch.utils.data import DataLoader
 
 from . import ops
 from ._lib import GtsError
+from .data_loader import DevicePrefetcher
 from .graph import minibatch_graphs
 from .networks import init_graph_net
 from .project import project_nodes_to_img
@@ -58,7 +59,10 @@ class GNN:
     def run_epoch(self):
         self.net.train()
         losses = []
-        for batch_mris, batch_graphs, batch_features, batch_labels in self.train_loader:
+        # self.prefetch = True stages batch i+1 (H2D + CSR build) on a side stream while batch i computes; the default
+        # keeps the reference's in-stream .to(device) (model/gnn_model.py:38-40)
+        loader = DevicePrefetcher(self.train_loader, self.device) if getattr(self, "prefetch", False) else self.train_loader
+        for batch_mris, batch_graphs, batch_features, batch_labels in loader:
             batch_graphs = batch_graphs.to(self.device)
             batch_features = batch_features.to(self.device)
             batch_labels = batch_labels.to(self.device)

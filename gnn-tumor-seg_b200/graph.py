@@ -115,6 +115,23 @@ class BatchedGraph:
     def cuda(self):
         return self.to("cuda")
 
+    def device_tensors(self):
+        """Every device tensor this graph owns (CSR, edge lists, lazily built CSC, error flag, ndata)."""
+        out = [t for t in (getattr(self, "_gsrc", None), getattr(self, "_gdst", None), getattr(self, "_eid", None),
+                           getattr(self, "err_flag", None)) if torch.is_tensor(t) and t.is_cuda]
+        for grp in (self._csr, getattr(self, "_csc", None)):
+            if grp is not None:
+                out += [t for t in grp if torch.is_tensor(t) and t.is_cuda]
+        out += [t for t in self.ndata.values() if torch.is_tensor(t) and t.is_cuda]
+        return out
+
+    def record_stream(self, stream):
+        """Tell the caching allocator that ``stream`` uses this graph's tensors (they were staged on another stream:
+        data_loader.DevicePrefetcher)."""
+        for t in self.device_tensors():
+            t.record_stream(stream)
+        return self
+
     @property
     def csr(self):
         """(indptr int32[N+1], indices int32[E]) — in-edges by destination."""

@@ -191,3 +191,56 @@ def determine_tumor_crop(svs, node_classes_or_logits):
     if not any(f.any() for f in flags):                   # nothing predicted tumorous: the whole (uncropped) volume
         flags = [np.ones(n, dtype=bool) for n in (X, Y, Z)]
     return np.ix_(*flags)
+
+
+class VolumeDownloader:
+    """Ring of (device volume, pinned host volume) pairs with a private copy stream.
+
+    ``generate_gnn_predictions`` (scripts/generate_gnn_predictions.py:43-52,64-73) produces one (240,240,155) int16
+    label volume per MRI and hands it to the host (NIfTI write).  17.9 MB per volume over PCIe costs as much as the
+    whole eval forward of the graph, so copying on the compute stream halves the throughput of bulk inference; here the
+    device->host copy of volume i runs on its own stream while graph i+1 computes.
+
+        dl = VolumeDownloader(depth=3)
+        for ...:
+            slot, vol = dl.acquire()                       # compute stream waits until the slot's last copy is done
+            project_labels_to_brats(..., out=vol, ...)
+            dl.submit(slot)                                # D2H on the copy stream, after the kernels enqueued so far
+            ...
+            host = dl.wait(slot)                           # pinned host tensor, valid until the slot is acquired again
+    """
+
+    def __init__(self, depth=3, shape=BRATS_SHAPE, dtype=torch.int16, device=None):
+        self.device = torch.device(device) if device is not None else _device()
+        self.depth = max(1, int(depth))
+        self.dev = [torch.empty(shape, dtype=dtype, device=self.device) for _ in range(self.depth)]
+        self.host = [torch.empty(shape, dtype=dtype).pin_memory() for _ in range(self.depth)]
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._done = [None] * self.depth
+        self._next = 0
+
+    def acquire(self):
+        slot = self._next
+        self._next = (self._next + 1) % self.depth
+        if self._done[slot] is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._done[slot])
+        return slot, self.dev[slot]
+
+    def submit(self, slot):
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            self.host[slot].copy_(self.dev[slot], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self._done[slot] = done
+
+    def wait(self, slot):
+        if self._done[slot] is not None:
+            self._done[slot].synchronize()
+        return self.host[slot]
+
+    def drain(self):
+        self.stream.synchronize()
+

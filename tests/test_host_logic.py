@@ -140,3 +140,17 @@ def test_product_package_never_imports_oracle():
         if fn.endswith(".py"):
             txt = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), fn
+
+
+def test_overlap_helpers_fail_loudly_without_cuda():
+    """DevicePrefetcher / VolumeDownloader are CUDA-stream helpers: no silent CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from gnn_tumor_seg_b200 import project
+    from gnn_tumor_seg_b200._lib import GtsError
+    from gnn_tumor_seg_b200.data_loader import DevicePrefetcher
+    with pytest.raises(GtsError):
+        DevicePrefetcher([], "cuda")
+    with pytest.raises(GtsError):
+        project.VolumeDownloader()
