@@ -25,6 +25,7 @@
 // fp32-accurate).
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cstdlib>
 
 namespace gts {
@@ -873,11 +874,63 @@ __device__ __forceinline__ void mma_x3_block_ts2(uint32_t d_tmem, uint32_t a_hi,
       ::"r"(d_tmem), "r"(a_hi), "r"(b_lo32), "r"(l_lo32), "r"(desc_hi32), "r"(k16), "r"(idesc), "r"(first) : "memory");
 }
 
-template <bool TN, bool DUAL>
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+// D = f32, A = B = bf16 (kind::f16), A in TMEM (K-major), B K-major
+__host__ __device__ constexpr uint32_t make_idesc_ts_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo_elem, hi_elem);     // .x (low half) = even k, .y = odd k
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// "BF" form of the k-block (NT only): hi*hi stays a TF32 product of the raw fp32 operands (4 MMAs, K = 8 each), the
+// two cross terms A_lo*B and A*B_lo run as bf16 MMAs (kind::f16, K = 16 each: 2 + 2 MMAs) at twice the tensor rate:
+// 8 MMAs per k-block instead of 12.  The factors of the cross terms only need ~8 bits (they multiply a 2^-11 term:
+// error ~2^-20 relative, below the fp32 accumulation error of the tensor core that bounds this mode).
+// TMEM slot (64 columns): [0,32) A fp32 | [32,48) bf16x2(A_lo) | [48,64) bf16x2(A);  shared memory: B fp32 tile, then
+// one 128-byte-row tile [bf16(B) k 0..31 | bf16(B_lo) k 0..31] with the same 128B swizzle.
+__device__ __forceinline__ void mma_x3bf_block_ts2(uint32_t d_tmem, uint32_t a_hi, uint32_t b_lo32, uint32_t l_lo32,
+                                                   uint32_t desc_hi32, uint32_t idesc, uint32_t idesc_bf, uint32_t first) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pf, pt, pe;\n\t"
+      ".reg .b32 x1, x2, x3, y1, y2, y3, ah1, ah2, ah3, al0, al1, ab0, ab1;\n\t"
+      ".reg .b64 b0, b1, b2, b3, h0, h1, l0, l1;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pf, %7, 0;\n\t"
+      "setp.eq.b32 pt, %7, %7;\n\t"
+      "add.u32 x1, %2, 2;\n\t add.u32 x2, %2, 4;\n\t add.u32 x3, %2, 6;\n\t"
+      "add.u32 y1, %3, 2;\n\t add.u32 y2, %3, 4;\n\t add.u32 y3, %3, 6;\n\t"
+      "mov.b64 b0, {%2, %4};\n\t mov.b64 b1, {x1, %4};\n\t mov.b64 b2, {x2, %4};\n\t mov.b64 b3, {x3, %4};\n\t"
+      "mov.b64 h0, {%3, %4};\n\t mov.b64 h1, {y1, %4};\n\t mov.b64 l0, {y2, %4};\n\t mov.b64 l1, {y3, %4};\n\t"
+      "add.u32 ah1, %1, 8;\n\t add.u32 ah2, %1, 16;\n\t add.u32 ah3, %1, 24;\n\t"
+      "add.u32 al0, %1, 32;\n\t add.u32 al1, %1, 40;\n\t add.u32 ab0, %1, 48;\n\t add.u32 ab1, %1, 56;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], b0, %5, pf;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [ah1], b1, %5, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [ah2], b2, %5, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [ah3], b3, %5, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], [al0], h0, %6, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], [al1], h1, %6, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], [ab0], l0, %6, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], [ab1], l1, %6, pt;\n\t"
+      "}"
+      ::"r"(d_tmem), "r"(a_hi), "r"(b_lo32), "r"(l_lo32), "r"(desc_hi32), "r"(idesc), "r"(idesc_bf), "r"(first) : "memory");
+}
+
+template <bool TN, bool DUAL, bool BF = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Ts2Cfg::THREADS, 1)
 gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, const Params p) {
   static_assert(!DUAL || TN, "the two-B form exists for the weight-gradient GEMM only");
+  static_assert(!BF || !TN, "bf16 cross terms: NT form only");
   using L = Ts2CfgT<DUAL>;
   constexpr int NB = L::NB;
   constexpr int STAGES = L::STAGES;
@@ -981,6 +1034,7 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     if (rank == 0) {
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);          // warp-uniform copy
       const uint32_t idesc = make_idesc_ts(2 * BM, p.BN, TN);
+      const uint32_t idesc_bf = make_idesc_ts_bf16(2 * BM, p.BN);
       // descriptor of a B tile at shared-memory address 0; the address field (bits 0..13, 16-byte units) is added per use
       const uint64_t desc0 = make_smem_desc(0, TN ? 4096 : 16, TN ? 512 : 1024, TN ? kLayoutSw128Base32 : kLayoutSw128);
       const uint32_t desc0_lo = (uint32_t)desc0, desc0_hi = (uint32_t)(desc0 >> 32);
@@ -1008,6 +1062,10 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
               const uint32_t bb = b_lo32 + (uint32_t)b * (2 * L::B_HALF_BYTES >> 4);
+              if (BF)
+                mma_x3bf_block_ts2(d_tmem, a_hi, bb, bb + (L::B_HALF_BYTES >> 4), desc0_hi, idesc, idesc_bf,
+                                   (kb > kb_beg || j > 0) ? 1u : 0u);
+              else
               mma_x3_block_ts2(d_tmem + (uint32_t)b * L::BN_MAX, a_hi, bb, bb + (L::B_HALF_BYTES >> 4), desc0_hi, koff16, idesc,
                                (kb > kb_beg || j > 0) ? 1u : 0u);
             }
@@ -1058,15 +1116,30 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
               csum += x;
             }
           }
+          uint32_t lob[16], hib[16];
+          if (BF) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) lo[i] = __float_as_uint(tf32_lo(__uint_as_float(hi[i])));
+            for (int i = 0; i < 16; ++i) {
+              const float x0 = __uint_as_float(hi[2 * i]), x1 = __uint_as_float(hi[2 * i + 1]);
+              lob[i] = pack_bf16x2(x0 - __uint_as_float(hi[2 * i] & 0xFFFFE000u), x1 - __uint_as_float(hi[2 * i + 1] & 0xFFFFE000u));
+              hib[i] = pack_bf16x2(x0, x1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) lo[i] = __float_as_uint(tf32_lo(__uint_as_float(hi[i])));
+          }
           if (j == 0) {
             mbar_wait(&a_free[slot], sphase ^ 1);      // the MMAs that read this TMEM slot have retired
             tcgen05_fence_after();
           }
           const uint32_t t_a = tmem_base + ((uint32_t)(q * 32) << 16) + L::A_COL0 + (uint32_t)(slot * KSUB + j) * 64;
           tmem_st_32x32b_x32(t_a, hi);
-          tmem_st_32x32b_x32(t_a + 32, lo);
+          if (BF) {
+            tmem_st_32x32b_x16(t_a + 32, lob);
+            tmem_st_32x32b_x16(t_a + 48, hib);
+          } else {
+            tmem_st_32x32b_x32(t_a + 32, lo);
+          }
         }
         tmem_st_wait();
         tcgen05_fence_before();
@@ -1100,10 +1173,31 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
               uint8_t* bt = smem + stage * STAGE_BYTES + j * SUB_BYTES + A_STAGE_BYTES + b * 2 * L::B_HALF_BYTES;
               const float4* hi = reinterpret_cast<const float4*>(bt);
               float4* lo = reinterpret_cast<float4*>(bt + L::B_HALF_BYTES);
+              if (BF) {
+                // row n (128 B, 16-byte chunk c stored at c ^ (n & 7)): fp32 chunks 2d, 2d+1 (k = 8d .. 8d+7) ->
+                // bf16(B) into chunk d and bf16(B_lo) into chunk 4 + d of the same row of the second tile
+                for (int i = t; i < half_bn * 4; i += 128) {
+                  const int n = i >> 2, d = i & 3, sw = n & 7;
+                  const float4 x = hi[n * 8 + ((2 * d) ^ sw)], y = hi[n * 8 + ((2 * d + 1) ^ sw)];
+                  const float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+                  uint32_t hb[4], lb[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float a0 = v[2 * e], a1 = v[2 * e + 1];
+                    hb[e] = pack_bf16x2(a0, a1);
+                    lb[e] = pack_bf16x2(a0 - __uint_as_float(__float_as_uint(a0) & 0xFFFFE000u),
+                                        a1 - __uint_as_float(__float_as_uint(a1) & 0xFFFFE000u));
+                  }
+                  uint4* row = reinterpret_cast<uint4*>(lo) + n * 8;
+                  row[d ^ sw] = make_uint4(hb[0], hb[1], hb[2], hb[3]);
+                  row[(4 + d) ^ sw] = make_uint4(lb[0], lb[1], lb[2], lb[3]);
+                }
+              } else {
 #pragma unroll 4
               for (int i = t; i < n_vec; i += 128) {
                 const float4 x = hi[i];
                 lo[i] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+              }
               }
             }
           }
@@ -1233,19 +1327,19 @@ static int launch_ts(const CUtensorMap& a1, const CUtensorMap& a2, const CUtenso
   return GTS_OK;
 }
 
-template <bool TN, bool DUAL = false>
+template <bool TN, bool DUAL = false, bool BF = false>
 static int launch_ts2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1, const CUtensorMap& b2,
                       const Params& p, int n_work, cudaStream_t st) {
   using L = Ts2CfgT<DUAL>;
   static bool done = false;
   if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_x3ts2_kernel<TN, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::dyn_bytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_x3ts2_kernel<TN, DUAL, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::dyn_bytes);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d) failed: %s", L::dyn_bytes, cudaGetErrorString(e)); return GTS_ERR_CUDA; }
     done = true;
   }
   const int pairs = sm_count() / 2;
   const int grid = 2 * (n_work < pairs ? n_work : pairs);          // one CTA pair (cluster of 2) per TPC
-  gemm_x3ts2_kernel<TN, DUAL><<<grid, L::THREADS, L::dyn_bytes, st>>>(a1, a2, b1, b2, p);
+  gemm_x3ts2_kernel<TN, DUAL, BF><<<grid, L::THREADS, L::dyn_bytes, st>>>(a1, a2, b1, b2, p);
   GTS_LAUNCH_CHECK();
   return GTS_OK;
 }
@@ -1317,6 +1411,11 @@ int gemm_nt_tcgen05(const gts_gemm_nt_args* a, cudaStream_t st) {
     tA2 = tA1; tB2 = tB1;
   }
   const int n_work = p.tiles_m * p.tiles_n;
+  // cross terms of the 3xTF32 scheme as bf16 MMAs (8 instead of 12 MMAs per k-block; GTS_X3_BF16=0: all-TF32 form).
+  // Measured: same error against fp64 (2.7e-6 max on K=256 products, logits 2.6e-5 on the 8-layer stack), K=256
+  // 59.8 -> 55.9 us, K=512 100.6 -> 98.3 us, training step 5.19 -> 5.10 ms.
+  static const bool bf_cross = !(getenv("GTS_X3_BF16") && atoi(getenv("GTS_X3_BF16")) == 0);    // default on
+  if (pair && bf_cross) return launch_ts2<false, false, true>(tA1, tA2, tB1, tB2, p, n_work, st);
   if (pair) return launch_ts2<false>(tA1, tA2, tB1, tB2, p, n_work, st);
   if (in_tmem)
     return ts_bn_cap() == 256 ? launch_ts<false, 256>(tA1, tA2, tB1, tB2, p, n_work, st)
