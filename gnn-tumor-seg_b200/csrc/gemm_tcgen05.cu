@@ -780,13 +780,14 @@ gemm_x3ts_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
 // ---------------------------------------------------------------------------
 // DUAL (weight gradients only): one A operand against TWO B operands per ring slot (dWs = dZ^T h and dWn = dZ^T neigh
 // share dZ): the split A tile in TMEM feeds 24 instead of 12 MMAs, into two accumulators.
-template <bool DUAL>
+template <bool DUAL, int BF = 0>
 struct Ts2CfgT {
   static constexpr int NB = DUAL ? 2 : 1;                                // B operands per slot
   static constexpr int BN_MAX = 128;                                   // UMMA N of a pair tile
   static constexpr int KSUB = 1;                                       // k-blocks (of 32) per ring slot: one barrier round per 24 MMAs
   static constexpr int STAGES = DUAL ? 4 : 6;                          // shared-memory ring
-  static constexpr int A_SLOTS = 4;                                    // TMEM ring of split A tiles
+  static constexpr int SLOT_COLS = BF == 2 ? 32 : 64;                  // BF == 2: only the bf16 parts of A live in TMEM
+  static constexpr int A_SLOTS = BF == 2 ? 8 : 4;                      // TMEM ring of split A tiles
   static constexpr int ACC_BUFS = 2;
   static constexpr int EPI_WARPS = 4;
   static constexpr int B_HALF_BYTES = (BN_MAX / 2) * BK * 4;           // 8 KB: this CTA's half of the N rows
@@ -801,7 +802,7 @@ struct Ts2CfgT {
   static constexpr int dyn_bytes = total + 1024;
   static_assert(dyn_bytes <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
   static constexpr uint32_t A_COL0 = ACC_BUFS * BN_MAX;                // 256
-  static_assert(A_COL0 + 64 * KSUB * A_SLOTS <= TMEM_COLS, "TMEM column budget");
+  static_assert(A_COL0 + SLOT_COLS * KSUB * A_SLOTS <= TMEM_COLS, "TMEM column budget");
 };
 using Ts2Cfg = Ts2CfgT<false>;
 
@@ -925,13 +926,47 @@ __device__ __forceinline__ void mma_x3bf_block_ts2(uint32_t d_tmem, uint32_t a_h
       ::"r"(d_tmem), "r"(a_hi), "r"(b_lo32), "r"(l_lo32), "r"(desc_hi32), "r"(idesc), "r"(idesc_bf), "r"(first) : "memory");
 }
 
-template <bool TN, bool DUAL, bool BF = false>
+// BF == 2: as above, but the hi*hi TF32 product reads A straight from the TMA-landed shared-memory tile (SS form:
+// the raw fp32 tile IS the hi operand, the MMA truncates it), so a TMEM slot holds only the two bf16 parts
+// ([0,16) bf16x2(A_lo) | [16,32) bf16x2(A)) and the ring is 8 slots deep instead of 4.
+__device__ __forceinline__ void mma_x3bf2_block_ts2(uint32_t d_tmem, uint32_t a_tm, uint32_t a_lo32, uint32_t b_lo32,
+                                                    uint32_t l_lo32, uint32_t desc_hi32, uint32_t idesc, uint32_t idesc_bf,
+                                                    uint32_t first) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pf, pt, pe;\n\t"
+      ".reg .b32 x1, x2, x3, y1, y2, y3, z1, z2, z3, al1, ab0, ab1;\n\t"
+      ".reg .b64 a0, a1, a2, a3, b0, b1, b2, b3, h0, h1, l0, l1;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pf, %8, 0;\n\t"
+      "setp.eq.b32 pt, %8, %8;\n\t"
+      "add.u32 x1, %3, 2;\n\t add.u32 x2, %3, 4;\n\t add.u32 x3, %3, 6;\n\t"
+      "add.u32 y1, %4, 2;\n\t add.u32 y2, %4, 4;\n\t add.u32 y3, %4, 6;\n\t"
+      "add.u32 z1, %2, 2;\n\t add.u32 z2, %2, 4;\n\t add.u32 z3, %2, 6;\n\t"
+      "mov.b64 a0, {%2, %5};\n\t mov.b64 a1, {z1, %5};\n\t mov.b64 a2, {z2, %5};\n\t mov.b64 a3, {z3, %5};\n\t"
+      "mov.b64 b0, {%3, %5};\n\t mov.b64 b1, {x1, %5};\n\t mov.b64 b2, {x2, %5};\n\t mov.b64 b3, {x3, %5};\n\t"
+      "mov.b64 h0, {%4, %5};\n\t mov.b64 h1, {y1, %5};\n\t mov.b64 l0, {y2, %5};\n\t mov.b64 l1, {y3, %5};\n\t"
+      "add.u32 al1, %1, 8;\n\t add.u32 ab0, %1, 16;\n\t add.u32 ab1, %1, 24;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], a0, b0, %6, pf;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], a1, b1, %6, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], a2, b2, %6, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], a3, b3, %6, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], h0, %7, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], [al1], h1, %7, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], [ab0], l0, %7, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], [ab1], l1, %7, pt;\n\t"
+      "}"
+      ::"r"(d_tmem), "r"(a_tm), "r"(a_lo32), "r"(b_lo32), "r"(l_lo32), "r"(desc_hi32), "r"(idesc), "r"(idesc_bf), "r"(first)
+      : "memory");
+}
+
+template <bool TN, bool DUAL, int BF = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Ts2Cfg::THREADS, 1)
 gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, const Params p) {
   static_assert(!DUAL || TN, "the two-B form exists for the weight-gradient GEMM only");
   static_assert(!BF || !TN, "bf16 cross terms: NT form only");
-  using L = Ts2CfgT<DUAL>;
+  using L = Ts2CfgT<DUAL, BF>;
   constexpr int NB = L::NB;
   constexpr int STAGES = L::STAGES;
   constexpr int A_SLOTS = L::A_SLOTS;
@@ -1058,11 +1093,14 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
           const int nsub = min(KSUB, kb_end - kb);
           for (int j = 0; j < nsub; ++j) {
             const uint32_t b_lo32 = desc0_lo + sb0 + (uint32_t)(stage * STAGE_BYTES + j * SUB_BYTES) / 16;
-            const uint32_t a_hi = tmem_u + L::A_COL0 + (uint32_t)(slot * KSUB + j) * 64;
+            const uint32_t a_hi = tmem_u + L::A_COL0 + (uint32_t)(slot * KSUB + j) * L::SLOT_COLS;
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
               const uint32_t bb = b_lo32 + (uint32_t)b * (2 * L::B_HALF_BYTES >> 4);
-              if (BF)
+              if (BF == 2)     // A tile of this stage: same descriptor fields as a K-major B tile (128 rows instead of 64)
+                mma_x3bf2_block_ts2(d_tmem, a_hi, bb - (A_STAGE_BYTES >> 4), bb, bb + (L::B_HALF_BYTES >> 4), desc0_hi,
+                                    make_idesc(2 * BM, p.BN, false), idesc_bf, (kb > kb_beg || j > 0) ? 1u : 0u);
+              else if (BF == 1)
                 mma_x3bf_block_ts2(d_tmem, a_hi, bb, bb + (L::B_HALF_BYTES >> 4), desc0_hi, idesc, idesc_bf,
                                    (kb > kb_beg || j > 0) ? 1u : 0u);
               else
@@ -1132,9 +1170,12 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
             mbar_wait(&a_free[slot], sphase ^ 1);      // the MMAs that read this TMEM slot have retired
             tcgen05_fence_after();
           }
-          const uint32_t t_a = tmem_base + ((uint32_t)(q * 32) << 16) + L::A_COL0 + (uint32_t)(slot * KSUB + j) * 64;
-          tmem_st_32x32b_x32(t_a, hi);
-          if (BF) {
+          const uint32_t t_a = tmem_base + ((uint32_t)(q * 32) << 16) + L::A_COL0 + (uint32_t)(slot * KSUB + j) * L::SLOT_COLS;
+          if (BF != 2) tmem_st_32x32b_x32(t_a, hi);
+          if (BF == 2) {
+            tmem_st_32x32b_x16(t_a, lob);
+            tmem_st_32x32b_x16(t_a + 16, hib);
+          } else if (BF == 1) {
             tmem_st_32x32b_x16(t_a + 32, lob);
             tmem_st_32x32b_x16(t_a + 48, hib);
           } else {
@@ -1327,10 +1368,10 @@ static int launch_ts(const CUtensorMap& a1, const CUtensorMap& a2, const CUtenso
   return GTS_OK;
 }
 
-template <bool TN, bool DUAL = false, bool BF = false>
+template <bool TN, bool DUAL = false, int BF = 0>
 static int launch_ts2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1, const CUtensorMap& b2,
                       const Params& p, int n_work, cudaStream_t st) {
-  using L = Ts2CfgT<DUAL>;
+  using L = Ts2CfgT<DUAL, BF>;
   static bool done = false;
   if (!done) {
     cudaError_t e = cudaFuncSetAttribute(gemm_x3ts2_kernel<TN, DUAL, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::dyn_bytes);
@@ -1414,8 +1455,9 @@ int gemm_nt_tcgen05(const gts_gemm_nt_args* a, cudaStream_t st) {
   // cross terms of the 3xTF32 scheme as bf16 MMAs (8 instead of 12 MMAs per k-block; GTS_X3_BF16=0: all-TF32 form).
   // Measured: same error against fp64 (2.7e-6 max on K=256 products, logits 2.6e-5 on the 8-layer stack), K=256
   // 59.8 -> 55.9 us, K=512 100.6 -> 98.3 us, training step 5.19 -> 5.10 ms.
-  static const bool bf_cross = !(getenv("GTS_X3_BF16") && atoi(getenv("GTS_X3_BF16")) == 0);    // default on
-  if (pair && bf_cross) return launch_ts2<false, false, true>(tA1, tA2, tB1, tB2, p, n_work, st);
+  static const int bf_cross = getenv("GTS_X3_BF16") ? atoi(getenv("GTS_X3_BF16")) : 1;    // default on
+  if (pair && bf_cross == 2) return launch_ts2<false, false, 2>(tA1, tA2, tB1, tB2, p, n_work, st);
+  if (pair && bf_cross == 1) return launch_ts2<false, false, 1>(tA1, tA2, tB1, tB2, p, n_work, st);
   if (pair) return launch_ts2<false>(tA1, tA2, tB1, tB2, p, n_work, st);
   if (in_tmem)
     return ts_bn_cap() == 256 ? launch_ts<false, 256>(tA1, tA2, tB1, tB2, p, n_work, st)

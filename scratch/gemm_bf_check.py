@@ -9,7 +9,7 @@ torch.manual_seed(0)
 N, D = 90000, 256
 A = [torch.randn(N, D, device=dev) for _ in range(3)]
 W1 = torch.randn(D, D, device=dev) / 16; W2 = torch.randn(D, D, device=dev) / 16; b = torch.randn(D, device=dev)
-tag = "bf16x" if os.environ.get("GTS_X3_BF16") == "1" else "tf32x3"
+tag = "x3_bf16=" + os.environ.get("GTS_X3_BF16", "default")
 for name, fn, ref in (
         ("k256", lambda i: ops.gemm_nt(A[i % 3], W1, mode="tf32x3"), lambda: A[0][:4096].double() @ W1.double().t()),
         ("k512", lambda i: ops.gemm_nt(A[i % 3], W1, A[(i + 1) % 3], W2, bias=b, act=1, mode="tf32x3"),
