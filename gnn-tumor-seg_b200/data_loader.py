@@ -173,13 +173,31 @@ class DevicePrefetcher:
         return staged
 
     def __iter__(self):
+        """Batch i+depth is staged before batch i is handed to the consumer."""
         from collections import deque
-        it = iter(self.batches)
-        q = deque()
-        for b in it:
-            q.append(self._stage(b))
-            if len(q) > self.depth:           # batch i+depth is staged before batch i is handed to the consumer
-                yield self._hand_over(*q.popleft())
-        while q:
-            yield self._hand_over(*q.popleft())
+        self._it = iter(self.batches)
+        self._q = deque()
+        self._explicit = False
+        while True:
+            if not self._explicit:
+                self.stage_next(self.depth + 1 - len(self._q))
+            if not self._q:
+                self.stage_next(1)
+                if not self._q:
+                    return
+            yield self._hand_over(*self._q.popleft())
 
+    def stage_next(self, n=None):
+        """Stage up to ``n`` more batches now (default: fill the queue to ``depth``).  A consumer that synchronises with
+        the device every step (``loss.item()``) calls this right AFTER enqueueing the step's kernels and BEFORE the
+        sync: the host-side staging work then overlaps the device's compute instead of delaying the step's first
+        kernel; once called, the iterator stops staging ahead on its own."""
+        if n is None:
+            self._explicit = True
+            n = self.depth - len(self._q)
+        for _ in range(max(0, n)):
+            try:
+                b = next(self._it)
+            except StopIteration:
+                return
+            self._q.append(self._stage(b))

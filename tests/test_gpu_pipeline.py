@@ -98,3 +98,16 @@ def test_volume_downloader_round_trip(cuda_dev):
         slots.append(slot)
     assert slots == [0, 1, 0, 1, 0]
     dl.drain()
+
+
+def test_prefetcher_explicit_stage_next(cuda_dev):
+    """The consumer-driven form: stage_next() after the step's kernels are enqueued; same batches, same order."""
+    batches = _host_batches(5, True)
+    pf = DevicePrefetcher(batches, cuda_dev)
+    got = []
+    for ids, dg, f, l in pf:
+        got.append((ids, int(dg.number_of_nodes()), float(f.sum())))
+        pf.stage_next()
+    assert [g[0] for g in got] == [b[0] for b in batches]
+    for g, b in zip(got, batches):
+        assert g[1] == b[1].number_of_nodes() and abs(g[2] - float(b[2].sum())) < 1e-2 * max(1.0, abs(float(b[2].sum())))
