@@ -182,3 +182,30 @@ def test_adamw_step_matches_torch(cuda_dev):
         _lib.check(lib.gts_adamw_step(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
                                       1e-2, 0.9, 0.999, 1e-8, 1e-2, t, 1.0, None, _lib.stream_ptr()))
     assert torch.allclose(p.cpu(), p_ref.detach(), atol=1e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("bf", ["0", "1", "2"])
+def test_gemm_nt_x3_cross_term_variants_against_fp64(cuda_dev, bf):
+    """GTS_X3_BF16 picks the form of the 3xTF32 cross terms in the CTA-pair NT kernel (0: all TF32, 1: bf16 MMAs -
+    the default, 2: bf16 + hi*hi from shared memory with an 8-slot TMEM ring).  The switch is read once per process,
+    so each variant runs in its own interpreter; all must stay fp32-accurate against an fp64 product."""
+    import os, subprocess, sys
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from gnn_tumor_seg_b200 import ops
+torch.manual_seed(0)
+dev = torch.device("cuda:0")
+M, K, N = 1000, 256, 256                       # M not a multiple of the 256-row pair tile
+A1, A2 = torch.randn(M, K, device=dev), torch.randn(M, K, device=dev) * 3
+W1, W2 = torch.randn(N, K, device=dev) / 16, torch.randn(N, K, device=dev) / 16
+b = torch.randn(N, device=dev)
+out = ops.gemm_nt(A1, W1, A2, W2, bias=b, act=0, mode="tf32x3")
+ref = A1.double() @ W1.double().t() + A2.double() @ W2.double().t() + b.double()
+err = ((out.double() - ref).abs().max() / ref.abs().max()).item()
+print("ERR", err)
+assert err < 2e-5, err
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GTS_X3_BF16=bf)
+    p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
