@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgts.so")
+LIB_PATH = os.environ.get("GTS_LIB_PATH") or os.path.join(_HERE, "libgts.so")     # override: A/B builds of the library
 
 GTS_OK = 0
 ACT_NONE, ACT_RELU, ACT_MASK_POS, ACT_MASK_POS_SCATTER = 0, 1, 2, 3
