@@ -377,7 +377,7 @@ def run_ours(args):
     ncu = load_ncu_traffic()
     kern["segmax_fwd"]["traffic"] = traffic_of(ncu, "segmax_fwd_pipe")
     kern["segmax_bwd"]["traffic"] = traffic_of(ncu, "segmax_bwd_vec")
-    kern["gemm_concat_k512"]["traffic"] = traffic_of(ncu, "gemm_x3ts2_kernel<0") if args.mode == "tf32x3" else None
+    kern["gemm_concat_k512"]["traffic"] = traffic_of(ncu, "gemm_x3ts2_kernel<0, 0, 1>", "gemm_x3ts2_kernel<0") if args.mode == "tf32x3" else None
     tot = sum(v["ms"] for v in breakdown.values()) or 1.0
     share = {k: {"ms": round(v["ms"], 4), "calls": v["calls"], "share": round(v["ms"] / tot, 4)}
              for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])}
@@ -391,7 +391,8 @@ def run_ours(args):
                     "traffic": kern["gemm_concat_k512"]["traffic"],
                     "executed_tflops": ach * passes,
                     "note": "algorithmic fwd+bwd flops of the step / summed GEMM launch time in the step (the tf32x3 mode "
-                            "executes 3 tensor-core passes per algorithmic flop: see executed_tflops); traffic = DRAM bytes of "
+                            "executes 3 tensor-core products per algorithmic flop - hi*hi in TF32 plus two cross terms, bf16 MMAs "
+                            "in the NT kernels, TF32 in the TN kernels: see executed_tflops); traffic = DRAM bytes of "
                             "one concat-GEMM launch (ncu); peak = 1/2 measured sustained bf16 (%s)" % peaks["src"]}
     else:
         k = kern["segmax_fwd"]
