@@ -66,14 +66,47 @@ def traffic_of(table, *needles):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock / throttle reasons DURING the timed region: NVML polled every 5 ms from a thread (a 100 ms region
+    gets ~20 samples); falls back to an `nvidia-smi -lms 100` loop when pynvml is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.nvml, self.samples, self.mask, self.run = None, [], 0, False
+        self.sm_max = None
+
+    def _poll(self):
+        n = self.nvml
+        while self.run:
+            try:
+                self.samples.append(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                self.mask |= int(self.get_reasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import pynvml as n
+            n.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber: resolve through the PCI bus id of the torch device
+            try:
+                bus = torch.cuda.get_device_properties(self.index).pci_bus_id
+                dom = torch.cuda.get_device_properties(self.index).pci_domain_id
+                dev = torch.cuda.get_device_properties(self.index).pci_device_id
+                self.h = n.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (dom, bus, dev)).encode())
+            except Exception:
+                self.h = n.nvmlDeviceGetHandleByIndex(self.index)
+            self.get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                n.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.sm_max = float(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM))
+            self.nvml, self.run = n, True
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -84,6 +117,18 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.nvml is not None:
+            self.run = False
+            self.t.join(timeout=2)
+            n = self.nvml
+            bits = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            reasons = sorted(k for k, b in bits.items() if self.mask & int(b))
+            sm = [float(x) for x in self.samples]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max,
+                    "samples": len(sm), "reasons": reasons, "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -102,7 +147,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def synth_batches(batch, n_batches, rank):
