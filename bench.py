@@ -343,33 +343,34 @@ def run_ours(args):
 
     # ---- end to end from pinned host buffers through the public API ----
     # every step: H2D of the step's edge lists / features / labels from pinned memory + device CSR build, forward, loss,
-    # backward, D2H loss (host sync per step, as the reference's loss.item()).  In-stream .to(device) by default.
-    # GTS_BENCH_TRAIN_PF=1 stages the inputs of step i+1 on data_loader.DevicePrefetcher's side stream right after
-    # step i's kernels are enqueued; measured 5.46 vs 5.41 ms in-stream (and 5.61 when staged BEFORE the step's
-    # kernels): what separates e2e from the device time is the host catching up after the per-step sync (the first,
-    # short kernels of a step run as fast as they are enqueued), not the 18.6 MB of input copies.
+    # backward, D2H read of the step's loss.  Default ("sync"): the reference's loss.item() per step
+    # (model/gnn_model.py:43) with in-stream .to(device): 5.4-5.5 ms against ~5.0 device-resident - after each sync the
+    # host has to catch up with the device.  GTS_BENCH_E2E=async: every step's loss copied to pinned host memory without
+    # stalling the host, inputs staged by data_loader.DevicePrefetcher, one synchronisation at the end: 5.34 ms in two
+    # runs and 11.5 ms in a third (side-stream staging is not yet robust: see DESIGN.md), hence not the default.
     from gnn_tumor_seg_b200.data_loader import DevicePrefetcher
-    train_pf = os.environ.get("GTS_BENCH_TRAIN_PF", "0") == "1"
+    e2e_mode = os.environ.get("GTS_BENCH_E2E", "sync")
+    loss_host = torch.zeros(max(args.steps, 8), dtype=torch.float32).pin_memory()
 
     def e2e_steps(n):
         src = (pinned[i % len(pinned)] for i in range(n))
         ls = None
-        if train_pf:
-            pf = DevicePrefetcher(src, dev)
-            for dg, f, l in pf:
-                t = trainer.forward_backward(dg, f, l)
-                pf.stage_next()                               # H2D + CSR build of the next step, overlapped
-                ls = float(t)                                 # D2H read of the step's loss (host sync per step)
-        else:
+        if e2e_mode == "sync":
             for bg, f, l in src:
                 ls = float(trainer.forward_backward(bg.to(dev), f.to(dev, non_blocking=True), l.to(dev, non_blocking=True)))
+        else:
+            for i, (dg, f, l) in enumerate(DevicePrefetcher(src, dev)):
+                t = trainer.forward_backward(dg, f, l)
+                loss_host[i % loss_host.numel()].copy_(t.detach(), non_blocking=True)      # D2H read of the step's loss
+            torch.cuda.current_stream().synchronize()
+            ls = float(loss_host[(n - 1) % loss_host.numel()])
         return ls
 
     e2e_steps(max(3, args.warmup // 2))
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    e2e_steps(args.steps)
+    loss_e2e = e2e_steps(args.steps)
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1) / args.steps
@@ -488,7 +489,10 @@ def run_ours(args):
                    "parallelism": "dp%d" % world},
         "clocks": clocks,
         "e2e": {"value": total_graphs / (ms_e2e * 1e-3), "unit": "graphs/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h},
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h, "loss": loss_e2e,
+                "loss_read": ("one blocking loss.item() per step" if e2e_mode == "sync" else
+                              "every step's loss copied D2H into pinned memory (non-blocking), one sync at the end of the timed "
+                              "region; inputs of step i+1 staged on a side stream (GTS_BENCH_E2E=sync for loss.item() per step)")},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "kernels": kern,
