@@ -52,7 +52,21 @@ class SageLayer(C.Structure):
 
 class SageLayerGrads(C.Structure):
     """struct gts_sage_layer_grads (include/gts.h)."""
-    _fields_ = [("dWp", C.c_void_p), ("dbp", C.c_void_p), ("dWs", C.c_void_p), ("dWn", C.c_void_p), ("db", C.c_void_p)]
+    _fields_ = [("dWp", C.c_void_p), ("dbp", C.c_void_p), ("dWs", C.c_void_p), ("dWn", C.c_void_p), ("db", C.c_void_p),
+                ("db2", C.c_void_p)]
+
+
+class SageStepArgs(C.Structure):
+    """struct gts_sage_step_args (include/gts.h)."""
+    _fields_ = [("layers", C.POINTER(SageLayer)), ("grads", C.POINTER(SageLayerGrads)), ("n_layers", C.c_int32),
+                ("n_nodes", C.c_int32),
+                ("indptr", C.c_void_p), ("indices", C.c_void_p), ("csc_indptr", C.c_void_p), ("csc_indices", C.c_void_p),
+                ("feats", C.c_void_p), ("ldf", C.c_int64),
+                ("labels", C.c_void_p), ("class_w", C.c_void_p),
+                ("sums", C.c_void_p),
+                ("logits", C.c_void_p), ("ldl", C.c_int64),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("mode", C.c_int32), ("normalize", C.c_int32), ("bwd_layer_lo", C.c_int32), ("reserved", C.c_int32)]
 
 
 # name -> (restype, argtypes); mirrors include/gts.h one to one
@@ -95,6 +109,11 @@ _SIGNATURES = {
     "gts_sage_backward": (C.c_int, [C.POINTER(SageLayer), C.POINTER(SageLayerGrads), C.c_int32, c_i32p, c_i32p,
                                     C.c_int32, c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_int64,
                                     C.c_void_p, C.c_size_t, C.c_int32, c_stream]),
+    "gts_sage_backward_range": (C.c_int, [C.POINTER(SageLayer), C.POINTER(SageLayerGrads), C.c_int32, C.c_int32, C.c_int32,
+                                          c_i32p, c_i32p, C.c_int32, c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p,
+                                          C.c_int64, C.c_void_p, C.c_size_t, C.c_int32, c_stream]),
+    "gts_sage_step": (C.c_int, [C.POINTER(SageStepArgs), c_stream]),
+    "gts_sage_step_backward_rest": (C.c_int, [C.POINTER(SageStepArgs), C.c_int32, C.c_int32, c_stream]),
     "gts_ce_weighted": (C.c_int, [c_f32p, C.c_int64, c_i64p, c_f32p, C.c_int32, C.c_int32, c_f32p, c_f32p,
                                   C.c_int64, c_stream]),
     "gts_scale_by_inv": (C.c_int, [c_f32p, C.c_int64, C.c_float, c_f32p, c_stream]),
@@ -125,6 +144,7 @@ _SIGNATURES = {
                                      C.c_void_p, C.c_size_t, c_stream]),
     "gts_adamw_step": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_float, C.c_float, C.c_float,
                                  C.c_float, C.c_float, C.c_int32, C.c_float, c_f32p, c_stream]),
+    "gts_adamw_step_dev": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, c_f32p, C.c_float, c_f32p, c_stream]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

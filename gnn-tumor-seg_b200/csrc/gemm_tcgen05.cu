@@ -199,7 +199,20 @@ struct Params {
   int splits; int kb_per_split; int kb_total; int64_t split_stride;
   int64_t c2_off;          // TN two-B form: offset (floats) of the second product inside a split record
   float* colsum_partial;   // TN, A-in-TMEM kernel: [splits][M] column sums of the A operand (or null)
+  long long* trace;        // GTS_TRACE builds only: per-CTA clock64 records of gemm_x3ntw_kernel (tools/gemm_trace.py)
+  int dbg;                 // GTS_TRACE builds only: ablation switches
 };
+
+// In-kernel trace (compile with -DGTS_TRACE; the shipped library has none of it): record r of CTA b at
+// trace[(b * kTraceItems + item) * kTraceSlots + r].
+#ifdef GTS_TRACE
+constexpr int kTraceItems = 8, kTraceSlots = 16;
+#define GTS_TR(item, r, val) do { if (p.trace && (item) < kTraceItems) p.trace[((long long)blockIdx.x * kTraceItems + (item)) * kTraceSlots + (r)] = (val); } while (0)
+#define GTS_TR_ON 1
+#else
+#define GTS_TR(item, r, val) do { (void)(item); } while (0)
+#define GTS_TR_ON 0
+#endif
 
 // ---------------------------------------------------------------------------
 // The kernel.  TN = false: NT form;  TN = true: weight-gradient form.
@@ -221,6 +234,12 @@ __device__ __forceinline__ float tf32_lo(float x) {
 // Epilogue of one accumulator tile for one warp: the warp owns TMEM lanes [q*32, q*32+32) (rows m0..m0+31 of C)
 // and the 32-column chunks c_first, c_first + c_step, ...  TMEM -> registers -> padded smem tile -> coalesced
 // 128-bit global stores with the fused bias / ReLU / ReLU-mask.
+#ifdef GTS_TRACE
+#define GTS_DBG(bit) (p.dbg & (1 << (bit)))     // timing-only ablation switches of the instrumented build (garbage results)
+#else
+#define GTS_DBG(bit) 0
+#endif
+
 template <bool TN>
 __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t t_base, int m0, int n0, float* Cout, float* stg,
                                               int lane, int c_first, int c_step, bool masked, uint64_t* full_bar,
@@ -245,9 +264,9 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t t_base, 
   tcgen05_fence_after();
   for (int c0 = c_first; c0 < p.BN; c0 += c_step) {
     uint32_t v[32];
-    tmem_ld_32x32b_x32(t_base + c0, v);
+    if (!GTS_DBG(2)) tmem_ld_32x32b_x32(t_base + c0, v);
     if (masked && c0 + c_step < p.BN) load_aux(c0 + c_step, aux_nxt);
-    tmem_ld_wait();
+    if (!GTS_DBG(2)) tmem_ld_wait();
     // lane = row: park the 32 columns of this row in the padded staging tile
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -259,8 +278,8 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t t_base, 
     const int col = n0 + c0 + cc;
     const bool col_ok = col < p.N && c0 + cc < p.BN;
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!TN && p.bias && col_ok) b = *reinterpret_cast<const float4*>(p.bias + col);
-    if (!TN && p.bias2 && col_ok) {
+    if (!TN && p.bias && col_ok && !GTS_DBG(1)) b = *reinterpret_cast<const float4*>(p.bias + col);
+    if (!TN && p.bias2 && col_ok && !GTS_DBG(1)) {
       const float4 b2 = *reinterpret_cast<const float4*>(p.bias2 + col);
       b.x += b2.x; b.y += b2.y; b.z += b2.z; b.w += b2.w;
     }
@@ -280,7 +299,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t t_base, 
             x.z = a.z > 0.f ? x.z : 0.f; x.w = a.w > 0.f ? x.w : 0.f;
           }
         }
-        *reinterpret_cast<float4*>(Cout + row * p.ldc + col) = x;
+        if (!GTS_DBG(0)) *reinterpret_cast<float4*>(Cout + row * p.ldc + col) = x;
       }
     }
     __syncwarp();
@@ -1286,6 +1305,518 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
   }
 }
 
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// Epilogue of one 128-column half tile for one warp of the wide kernel, FULL tiles only (all 32 rows inside M; N is
+// a multiple of 256, so every column is valid).
+//
+// What the in-kernel trace showed (profiles/r02_gemm_ntw.md): draining a half tile chunk by chunk (TMEM -> registers
+// -> padded smem -> coalesced stores) takes ~5000-7000 clk, and not because of the instruction count: all 148 SMs
+// drain at the same moment and 9.5 MB of stores go out at the ~3.5 TB/s the memory system accepts.  With the
+// accumulator held until its last chunk was stored, that burst sat on the MMA issuer's critical path (the R half of
+// the next item re-uses the accumulator).  Here the warp pulls its whole 32 x 128 slice into REGISTERS (128 per
+// thread; the epilogue warpgroup raises its register budget with setmaxnreg), hands the accumulator back at once,
+// and then stores at whatever rate the memory system takes while the next item's MMAs run.
+// Row pointers are formed once, chunk offsets are immediates, bias is fetched before the accumulator wait, the
+// ReLU-mask operand is fetched one chunk ahead row by row (no second register set).
+// ACT: GTS_ACT_NONE / GTS_ACT_RELU (bias, bias2 optional) / GTS_ACT_MASK_POS (aux with ldaux == ldc, no bias).
+__device__ __forceinline__ void sts_128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds_128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+template <int ACT>
+__device__ __forceinline__ void epilogue_half_regs(const Params& p, uint32_t t_base, int m0, int n0, float* stg, int lane,
+                                                   uint64_t* full_bar, uint32_t full_phase, uint64_t* empty_local,
+                                                   uint32_t empty_remote, bool leader) {
+  const int cc = (lane & 7) * 4;
+  const int rsub = lane >> 3;
+  // explicit shared-state-space addresses: through a generic float* the compiler emitted generic LD / ST for the staging
+  // tile, which queue behind the outstanding global loads of the mask operand (seen: 14 000+ clk per masked half tile)
+  const uint32_t stg_w = smem_u32(stg) + (uint32_t)(lane * EPI_LD) * 4;                 // this lane's row (write side)
+  const uint32_t stg_r = smem_u32(stg) + (uint32_t)(rsub * EPI_LD + cc) * 4;            // row rsub, columns cc.. (read side)
+  float* c_row = p.C + (int64_t)(m0 + rsub) * p.ldc + n0 + cc;       // row m0 + rsub; row 4j + rsub is j * step4 further
+  const int step4 = 4 * (int)p.ldc;                                    // 32-bit element offsets: one IMAD.WIDE per access
+  const float* a_row = ACT == GTS_ACT_MASK_POS ? p.aux + (int64_t)(m0 + rsub) * p.ldc + n0 + cc : nullptr;   // ldaux == ldc
+  float4 b[4];
+  if (ACT != GTS_ACT_MASK_POS) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      b[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias) b[c] = *reinterpret_cast<const float4*>(p.bias + n0 + 32 * c + cc);
+      if (p.bias2) {
+        const float4 b2 = *reinterpret_cast<const float4*>(p.bias2 + n0 + 32 * c + cc);
+        b[c].x += b2.x; b[c].y += b2.y; b[c].z += b2.z; b[c].w += b2.w;
+      }
+    }
+  }
+  // mask operand: two register sets, the loads of chunk c+1 all issued before chunk c is stored.  (Refilling aux[j]
+  // right after its use — one register set — serialised on the scoreboard: every LDS of the store loop then waited
+  // for the previous row's global load, 21 000 clk per half tile.)
+  float4 aux[2][8];
+  if (ACT == GTS_ACT_MASK_POS) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) aux[0][j] = ldg_nc_na(reinterpret_cast<const float4*>(a_row + j * step4));
+  }
+  mbar_wait(full_bar, full_phase);
+  tcgen05_fence_after();
+  uint32_t v[4][32];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(t_base + 32 * c, v[c]);
+  tmem_ld_wait();
+  tcgen05_fence_before();
+  __syncwarp();
+  if (lane == 0) { if (leader) mbar_arrive(empty_local); else mbar_arrive_remote(empty_remote); }   // accumulator free again
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (ACT == GTS_ACT_MASK_POS && c < 3) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        aux[(c + 1) & 1][j] = ldg_nc_na(reinterpret_cast<const float4*>(a_row + j * step4 + 32 * (c + 1)));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      sts_128(stg_w + 16 * j, v[c][4 * j], v[c][4 * j + 1], v[c][4 * j + 2], v[c][4 * j + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 x = lds_128(stg_r + j * (4 * EPI_LD * 4));
+      if (ACT == GTS_ACT_MASK_POS) {
+        const float4 a = aux[c & 1][j];
+        x.x = a.x > 0.f ? x.x : 0.f; x.y = a.y > 0.f ? x.y : 0.f;
+        x.z = a.z > 0.f ? x.z : 0.f; x.w = a.w > 0.f ? x.w : 0.f;
+      } else {
+        x.x += b[c].x; x.y += b[c].y; x.z += b[c].z; x.w += b[c].w;
+        if (ACT == GTS_ACT_RELU) {
+          x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+        }
+      }
+      if (!GTS_DBG(0)) *reinterpret_cast<float4*>(c_row + j * step4 + 32 * c) = x;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// NT "wide" form of the CTA-pair kernel (round 2): ONE pass over a 256-row A tile feeds BOTH 128-column halves of a
+// 256-wide output tile.
+//
+// Why (profiles/r01_gemm_x3_pipeline.md): the N = 128 pair kernel above fetches every A tile
+// twice per 256-wide output (once per N tile; 24 KB of TMA traffic per CTA for 512 clk of tensor work) and moves
+// 88 KB through shared memory per 512 clk; its time is the L2 -> SM operand delivery (TMA + barrier skeleton = 3/4 of
+// the kernel).  Here a k-block lands A (16 KB) once next to BOTH B halves (2 x 8 KB per CTA) and the split A tile in
+// TMEM feeds 16 MMAs instead of 8: 32 KB of TMA traffic and 144 KB of shared-memory traffic per 1024 clk of tensor
+// work, i.e. 1.5x / 1.25x less per flop.
+//
+// TMEM (512 columns): THREE 128-column accumulators, rotated over the half tiles (half tile h -> accumulator h % 3),
+// so the epilogue of item i (L half first, then R) overlaps the main loop of item i+1: the L half of item i+1 goes
+// to the spare accumulator, its R half re-uses the accumulator item i's L half drains first.  The A ring lives in
+// the remaining 128 columns as FOUR slots of HALF a k-block (16 k-values x 128 rows: 16 columns fp32 A | 8 columns
+// bf16x2(A_lo) | 8 columns bf16x2(A)): a slot feeds 2 x (2 TF32 + 2 bf16) MMAs = 512 clk, and three slots of tensor
+// work cover the hand-over (multicast commit -> a_free -> tcgen05.st -> remote arrive) of the fourth.
+// Shared memory: 4 stages of (A 16 | B_L fp32 8 | B_L bf16 8 | B_R fp32 8 | B_R bf16 8 KB) = 192 KB.
+// Warp roles (512 threads, warpgroup-aligned for setmaxnreg): 0 TMA, 1 MMA issuer (leader CTA), 2..3 idle,
+// 4..7 A split -> TMEM, 8..11 B split, 12..15 epilogue.
+// Requires N % 256 == 0 (each work item = 256 rows x 256 columns); other shapes stay on the N = 128 pair kernel.
+// ---------------------------------------------------------------------------
+struct NtwCfg {
+  static constexpr int STAGES = 4;
+  static constexpr int A_SLOTS = 4;                                    // TMEM ring of split half-k-block A tiles
+  static constexpr int SLOT_COLS = 32;
+  static constexpr int ACC_BUFS = 3;
+  static constexpr int BN_HALF = 128;                                  // UMMA N of one half tile
+  static constexpr int EPI_WARPS = 4;
+  static constexpr int B_HALF_BYTES = (BN_HALF / 2) * BK * 4;          // 8 KB: this CTA's 64 rows of one half tile
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + 2 * 2 * B_HALF_BYTES;   // 48 KB
+  // Roles are WARPGROUP-aligned so that setmaxnreg can move registers to where they are needed:
+  // warps 0..3: TMA producer (0), MMA issuer (1), two idle warps;  4..7: A split;  8..11: B split;  12..15: epilogue.
+  static constexpr int THREADS = 16 * 32;
+  static constexpr int REGS_CTRL = 80, REGS_ASPLIT = 104, REGS_BSPLIT = 72, REGS_EPI = 240;   // sum x 128 <= 64 K
+  static_assert(128 * (REGS_CTRL + REGS_ASPLIT + REGS_BSPLIT + REGS_EPI) <= 65536, "register file budget");
+  static constexpr int epi_off = STAGES * STAGE_BYTES;
+  static constexpr int epi_bytes = EPI_WARPS * 32 * EPI_LD * 4;
+  static constexpr int bar_off = epi_off + epi_bytes;
+  // full[S], empty[S], ready[A], a_free[A], tmem_full[3], tmem_empty[3], tmem_ptr
+  static constexpr int total = bar_off + (2 * STAGES + 2 * A_SLOTS + 2 * ACC_BUFS) * 8 + 16;
+  static constexpr int dyn_bytes = total + 1024;
+  static_assert(dyn_bytes <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
+  static constexpr uint32_t A_COL0 = ACC_BUFS * BN_HALF;               // 384
+  static_assert(A_COL0 + SLOT_COLS * A_SLOTS <= TMEM_COLS, "TMEM column budget");
+};
+
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+      : "memory");
+}
+
+// The four MMAs of HALF a k-block (16 k-values) into one 128-column half tile: hi*hi as two TF32 MMAs (K = 8) on the
+// raw fp32 operands, A_lo*B and A*B_lo as one bf16 MMA (K = 16) each.  a_tm: TMEM slot ([0,16) fp32 | [16,24)
+// bf16x2(A_lo) | [24,32) bf16x2(A)); b_lo32 / h_lo32: low descriptor words of the fp32 B tile at this half's first
+// k-step and of the bf16 tile [bf16(B) | bf16(B_lo)] at this half's 32-byte chunk.  Whole-warp call, one elected
+// lane issues (see mma_x3_block_ts2).
+__device__ __forceinline__ void mma_x3bf_half_ts2(uint32_t d_tmem, uint32_t a_tm, uint32_t b_lo32, uint32_t h_lo32,
+                                                  uint32_t desc_hi32, uint32_t idesc, uint32_t idesc_bf, uint32_t first) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pf, pt, pe;\n\t"
+      ".reg .b32 x1, y1, a1, a2, a3;\n\t"
+      ".reg .b64 b0, b1, h0, l0;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pf, %7, 0;\n\t"
+      "setp.eq.b32 pt, %7, %7;\n\t"
+      "add.u32 x1, %2, 2;\n\t"
+      "add.u32 y1, %3, 4;\n\t"
+      "mov.b64 b0, {%2, %4};\n\t mov.b64 b1, {x1, %4};\n\t"
+      "mov.b64 h0, {%3, %4};\n\t mov.b64 l0, {y1, %4};\n\t"
+      "add.u32 a1, %1, 8;\n\t add.u32 a2, %1, 16;\n\t add.u32 a3, %1, 24;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], b0, %5, pf;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [a1], b1, %5, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], [a2], h0, %6, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], [a3], l0, %6, pt;\n\t"
+      "}"
+      ::"r"(d_tmem), "r"(a_tm), "r"(b_lo32), "r"(h_lo32), "r"(desc_hi32), "r"(idesc), "r"(idesc_bf), "r"(first) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NtwCfg::THREADS, 1)
+gemm_x3ntw_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                  const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, const Params p) {
+  using L = NtwCfg;
+  constexpr int STAGES = L::STAGES;
+  constexpr int A_SLOTS = L::A_SLOTS;
+  constexpr int ACC_BUFS = L::ACC_BUFS;
+  constexpr int STAGE_BYTES = L::STAGE_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::bar_off);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* ready = full_bar + 2 * STAGES;           // leader's copy collects both CTAs' arrivals
+  uint64_t* a_free = ready + A_SLOTS;
+  uint64_t* tmem_full = a_free + A_SLOTS;
+  uint64_t* tmem_empty = tmem_full + ACC_BUFS;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + ACC_BUFS);
+  float* epi_stage = reinterpret_cast<float*>(smem + L::epi_off);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);    // provably warp-uniform
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();           // 0 = leader (issues the MMAs), 1 = peer
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+  const uint32_t smem_base = smem_u32(smem);         // operand tiles are read / written with explicit ld.shared / st.shared
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);                   // multicast commit of the leader
+    }
+    for (int s = 0; s < A_SLOTS; ++s) {
+      // even slots = first half of a k-block: 4 A-split + 4 B-split warps per CTA; odd slots: the A-split warps only
+      mbar_init(&ready[s], (s & 1) ? 8 : 16);
+      mbar_init(&a_free[s], 1);                      // multicast commit of the leader
+    }
+    for (int a = 0; a < ACC_BUFS; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 2 * L::EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&tmA1); prefetch_tmap(&tmB1);
+    if (p.kb2 > 0) { prefetch_tmap(&tmA2); prefetch_tmap(&tmB2); }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();                                // barriers initialised and TMEM allocated in BOTH CTAs
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // work item w -> (pair tile of 256 rows, 256-column tile); tiles_m counts 256-row pair tiles, tiles_n 256-column tiles
+  const int n_work = p.tiles_m * p.tiles_n;
+  const int n_kb = p.kb1 + p.kb2;
+  constexpr uint32_t stage_tx_bytes = (uint32_t)A_STAGE_BYTES + 2u * L::B_HALF_BYTES;
+
+  // Registers follow the roles (the epilogue warpgroup holds a 32 x 128 accumulator slice per warp).  Each setmaxnreg
+  // sits INSIDE its warpgroup's branch: ptxas sizes the register allocation of the code a setmaxnreg dominates, and a
+  // join after the four instructions would fall back to the launch bound (seen: 1184 bytes of spills).
+  if (warp < 4) {
+  setmaxnreg_dec<L::REGS_CTRL>();
+  if (warp == 0) {
+    // ======================= TMA producer (each CTA: its 128 rows of A, its 64 rows of each B half) =======================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = cluster_id; w < n_work; w += n_clusters) {
+        const int m0 = (w / p.tiles_n) * (2 * BM) + (int)rank * BM;
+        const int n0 = (w % p.tiles_n) * (2 * L::BN_HALF) + (int)rank * (L::BN_HALF / 2);
+        [[maybe_unused]] long long tr_empty = 0;
+        [[maybe_unused]] const int tr_item = (w - cluster_id) / n_clusters;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          if (GTS_TR_ON) { const long long t0 = clock64(); mbar_wait(&empty_bar[stage], phase ^ 1); tr_empty += clock64() - t0; }
+          else mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], stage_tx_bytes);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          const bool second = kb >= p.kb1;
+          const int k0 = (second ? kb - p.kb1 : kb) * BK;
+          tma_load_2d(sa, second ? &tmA2 : &tmA1, &full_bar[stage], k0, m0);
+          tma_load_2d(sb, second ? &tmB2 : &tmB1, &full_bar[stage], k0, n0);
+          tma_load_2d(sb + 2 * L::B_HALF_BYTES, second ? &tmB2 : &tmB1, &full_bar[stage], k0, n0 + L::BN_HALF);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        GTS_TR(tr_item, 6, tr_empty); GTS_TR(tr_item, 7, clock64());
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer (leader CTA only; the whole warp runs the loop, one elected lane issues) =======================
+    if (rank == 0) {
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);          // warp-uniform copy
+      const uint32_t idesc = make_idesc_ts(2 * BM, L::BN_HALF, false);
+      const uint32_t idesc_bf = make_idesc_ts_bf16(2 * BM, L::BN_HALF);
+      const uint64_t desc0 = make_smem_desc(0, 16, 1024, kLayoutSw128);
+      const uint32_t desc0_lo = (uint32_t)desc0, desc0_hi = (uint32_t)(desc0 >> 32);
+      const uint32_t sb0 = (smem_u32(smem) + A_STAGE_BYTES) >> 4;
+      const uint32_t empty0 = smem_u32(&empty_bar[0]), afree0 = smem_u32(&a_free[0]), tfull0 = smem_u32(&tmem_full[0]);
+      int stage = 0;
+      uint32_t slot_ctr = 0;                         // half k-blocks issued so far: slot = ctr & 3, phase = (ctr >> 2) & 1
+      uint32_t h = 0;                                // half tiles issued so far: accumulator = h % 3, use count = h / 3
+      for (int w = cluster_id; w < n_work; w += n_clusters, h += 2) {
+        const uint32_t accL = h % 3u, accR = (h + 1u) % 3u;
+        const uint32_t phL = ((h / 3u) & 1u) ^ 1u, phR = (((h + 1u) / 3u) & 1u) ^ 1u;
+        [[maybe_unused]] const int tr_item = (int)(h >> 1);
+        [[maybe_unused]] long long tr_ready = 0;
+        if (lane == 0) GTS_TR(tr_item, 0, clock64());
+        if (!mbar_test(&tmem_empty[accL], phL)) mbar_wait(&tmem_empty[accL], phL);   // drained by both CTAs' epilogues
+        tcgen05_fence_after();
+        if (lane == 0) GTS_TR(tr_item, 1, clock64());
+        const uint32_t dL = tmem_u + accL * L::BN_HALF, dR = tmem_u + accR * L::BN_HALF;
+        // The R half re-uses the accumulator that the previous item's L half drains FIRST; that drain is still in
+        // flight when this item starts.  Head of the item: the L-half MMAs of the first (up to) four half-k-block slots
+        // go out back to back (1024 clk of tensor work that needs only the spare accumulator and the A ring's
+        // depth), then the wait for the R accumulator, then the R-half MMAs of the same slots (which free them).
+        const int head_kb = n_kb < 2 ? n_kb : (GTS_DBG(4) ? 0 : 2);
+        const int stage_head = stage;
+        const uint32_t ctr_head = slot_ctr;
+        for (int kb = 0; kb < head_kb; ++kb) {
+          const uint32_t bL = desc0_lo + sb0 + (uint32_t)(stage * STAGE_BYTES) / 16;
+#pragma unroll
+          for (int hs = 0; hs < 2; ++hs, ++slot_ctr) {
+            const uint32_t slot = slot_ctr & (A_SLOTS - 1), sphase = (slot_ctr >> 2) & 1u;
+            if (GTS_TR_ON) {
+              const long long t0 = clock64();
+              if (!mbar_test(&ready[slot], sphase)) mbar_wait(&ready[slot], sphase);
+              tr_ready += clock64() - t0;
+            } else if (!mbar_test(&ready[slot], sphase)) mbar_wait(&ready[slot], sphase);
+            tcgen05_fence_after();
+            mma_x3bf_half_ts2(dL, tmem_u + L::A_COL0 + slot * L::SLOT_COLS, bL + 4u * hs,
+                              bL + (L::B_HALF_BYTES >> 4) + 2u * hs, desc0_hi, idesc, idesc_bf, (kb > 0 || hs > 0) ? 1u : 0u);
+          }
+          if (++stage == STAGES) stage = 0;
+        }
+        if (lane == 0) GTS_TR(tr_item, 2, clock64());
+        if (!mbar_test(&tmem_empty[accR], phR)) mbar_wait(&tmem_empty[accR], phR);
+        tcgen05_fence_after();
+        if (lane == 0) GTS_TR(tr_item, 3, clock64());
+        stage = stage_head;
+        slot_ctr = ctr_head;
+        for (int kb = 0; kb < head_kb; ++kb) {
+          const uint32_t bR = desc0_lo + sb0 + (uint32_t)(stage * STAGE_BYTES) / 16 + (2 * L::B_HALF_BYTES >> 4);
+#pragma unroll
+          for (int hs = 0; hs < 2; ++hs, ++slot_ctr) {
+            const uint32_t slot = slot_ctr & (A_SLOTS - 1);
+            mma_x3bf_half_ts2(dR, tmem_u + L::A_COL0 + slot * L::SLOT_COLS, bR + 4u * hs,
+                              bR + (L::B_HALF_BYTES >> 4) + 2u * hs, desc0_hi, idesc, idesc_bf, (kb > 0 || hs > 0) ? 1u : 0u);
+            tcgen05_commit_mc2_elect(afree0 + slot * 8);             // both CTAs: TMEM A slot (and its ready barrier) reusable
+          }
+          tcgen05_commit_mc2_elect(empty0 + (uint32_t)stage * 8);    // both CTAs: shared-memory stage reusable
+          if (++stage == STAGES) stage = 0;
+        }
+        for (int kb = head_kb; kb < n_kb; ++kb) {
+          const uint32_t bL = desc0_lo + sb0 + (uint32_t)(stage * STAGE_BYTES) / 16;   // fp32 tile of the L half
+          const uint32_t bR = bL + (2 * L::B_HALF_BYTES >> 4);
+#pragma unroll
+          for (int hs = 0; hs < 2; ++hs, ++slot_ctr) {
+            const uint32_t slot = slot_ctr & (A_SLOTS - 1), sphase = (slot_ctr >> 2) & 1u;
+            if (GTS_TR_ON) {
+              const long long t0 = clock64();
+              if (!mbar_test(&ready[slot], sphase)) mbar_wait(&ready[slot], sphase);
+              tr_ready += clock64() - t0;
+            } else if (!mbar_test(&ready[slot], sphase)) mbar_wait(&ready[slot], sphase);
+            tcgen05_fence_after();
+            const uint32_t a_tm = tmem_u + L::A_COL0 + slot * L::SLOT_COLS;
+            const uint32_t first = (kb > 0 || hs > 0) ? 1u : 0u;
+            mma_x3bf_half_ts2(dL, a_tm, bL + 4u * hs, bL + (L::B_HALF_BYTES >> 4) + 2u * hs, desc0_hi, idesc, idesc_bf, first);
+            mma_x3bf_half_ts2(dR, a_tm, bR + 4u * hs, bR + (L::B_HALF_BYTES >> 4) + 2u * hs, desc0_hi, idesc, idesc_bf, first);
+            tcgen05_commit_mc2_elect(afree0 + slot * 8);             // both CTAs: TMEM A slot (and its ready barrier) reusable
+          }
+          tcgen05_commit_mc2_elect(empty0 + (uint32_t)stage * 8);    // both CTAs: shared-memory stage reusable
+          if (++stage == STAGES) stage = 0;
+        }
+        tcgen05_commit_mc2_elect(tfull0 + accL * 8);                 // both CTAs: accumulators complete -> epilogue
+        tcgen05_commit_mc2_elect(tfull0 + accR * 8);
+        if (lane == 0) { GTS_TR(tr_item, 4, clock64()); GTS_TR(tr_item, 5, tr_ready); }
+      }
+    }
+  }   // warps 2, 3: idle
+  } else if (warp < 8) {
+    // ======================= A split -> TMEM (own 128 rows), two half-k-block slots per stage =======================
+    setmaxnreg_dec<L::REGS_ASPLIT>();
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    int stage = 0; uint32_t phase = 0;
+    uint32_t slot_ctr = 0;
+    const uint32_t ready_leader = mapa_u32(smem_u32(&ready[0]), 0);
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + L::A_COL0;
+    for (int w = cluster_id; w < n_work; w += n_clusters) {
+      [[maybe_unused]] long long tr_full = 0, tr_afree = 0;
+      for (int kb = 0; kb < n_kb; ++kb) {
+        if (GTS_TR_ON) { const long long t0 = clock64(); mbar_wait(&full_bar[stage], phase); tr_full += clock64() - t0; }
+        else mbar_wait(&full_bar[stage], phase);
+        // K-major tile, 128B swizzle: row r at r * 128, 16-byte chunk c stored at chunk c ^ (r & 7)
+        const uint32_t row = smem_base + (uint32_t)(stage * STAGE_BYTES + r * 128);      // shared-state-space address
+        uint32_t hi[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 x = lds_128(row + ((uint32_t)(c ^ (r & 7)) << 4));
+          hi[4 * c + 0] = __float_as_uint(x.x); hi[4 * c + 1] = __float_as_uint(x.y);
+          hi[4 * c + 2] = __float_as_uint(x.z); hi[4 * c + 3] = __float_as_uint(x.w);
+        }
+#pragma unroll
+        for (int hs = 0; hs < 2; ++hs, ++slot_ctr) {
+          uint32_t f32[16], lob[8], hib[8];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f32[i] = hi[16 * hs + i];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t u0 = hi[16 * hs + 2 * i], u1 = hi[16 * hs + 2 * i + 1];
+            const float x0 = __uint_as_float(u0), x1 = __uint_as_float(u1);
+            lob[i] = pack_bf16x2(x0 - __uint_as_float(u0 & 0xFFFFE000u), x1 - __uint_as_float(u1 & 0xFFFFE000u));
+            hib[i] = pack_bf16x2(x0, x1);
+          }
+          const uint32_t slot = slot_ctr & (A_SLOTS - 1), sphase = (slot_ctr >> 2) & 1u;
+          if (GTS_TR_ON) { const long long t0 = clock64(); mbar_wait(&a_free[slot], sphase ^ 1); tr_afree += clock64() - t0; }
+          else mbar_wait(&a_free[slot], sphase ^ 1);      // the MMAs that read this TMEM slot have retired
+          tcgen05_fence_after();
+          const uint32_t t_a = t_row + slot * L::SLOT_COLS;
+          tmem_st_32x32b_x16(t_a, f32);
+          tmem_st_32x32b_x8(t_a + 16, lob);
+          tmem_st_32x32b_x8(t_a + 24, hib);
+          tmem_st_wait();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (rank == 0) mbar_arrive(&ready[slot]); else mbar_arrive_remote(ready_leader + slot * 8); }
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (GTS_TR_ON && warp == 4 && lane == 0) {
+        const int tr_item = (w - cluster_id) / n_clusters;
+        GTS_TR(tr_item, 14, tr_full); GTS_TR(tr_item, 15, tr_afree);
+      }
+    }
+  } else if (warp < 12) {
+    // ======================= B split in shared memory (own 64 rows of both half tiles) =======================
+    setmaxnreg_dec<L::REGS_BSPLIT>();
+    const int t = threadIdx.x - 8 * 32;
+    int stage = 0; uint32_t phase = 0;
+    uint32_t slot_ctr = 0;
+    const uint32_t ready_leader = mapa_u32(smem_u32(&ready[0]), 0);
+    for (int w = cluster_id; w < n_work; w += n_clusters) {
+      for (int kb = 0; kb < n_kb; ++kb, slot_ctr += 2) {
+        mbar_wait(&full_bar[stage], phase);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const uint32_t hi = smem_base + (uint32_t)(stage * STAGE_BYTES + A_STAGE_BYTES + b * 2 * L::B_HALF_BYTES);
+          const uint32_t lo = hi + L::B_HALF_BYTES;
+          // row n (128 B, 16-byte chunk c stored at c ^ (n & 7)): fp32 chunks 2d, 2d+1 (k = 8d .. 8d+7) ->
+          // bf16(B) into chunk d and bf16(B_lo) into chunk 4 + d of the same row of the bf16 tile
+#pragma unroll
+          for (int i = t; i < (L::BN_HALF / 2) * 4; i += 128) {
+            const int n = i >> 2, d = i & 3, sw = n & 7;
+            const float4 x = lds_128(hi + (uint32_t)(n * 8 + ((2 * d) ^ sw)) * 16), y = lds_128(hi + (uint32_t)(n * 8 + ((2 * d + 1) ^ sw)) * 16);
+            const float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+            uint32_t hb[4], lb[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a0 = v[2 * e], a1 = v[2 * e + 1];
+              hb[e] = pack_bf16x2(a0, a1);
+              lb[e] = pack_bf16x2(a0 - __uint_as_float(__float_as_uint(a0) & 0xFFFFE000u),
+                                  a1 - __uint_as_float(__float_as_uint(a1) & 0xFFFFE000u));
+            }
+            const uint32_t orow = lo + (uint32_t)n * 128;
+            sts_128(orow + (uint32_t)(d ^ sw) * 16, hb[0], hb[1], hb[2], hb[3]);
+            sts_128(orow + (uint32_t)((4 + d) ^ sw) * 16, lb[0], lb[1], lb[2], lb[3]);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+        // the ready barrier is per A slot: do not arrive for round i before the phase of round i - A_SLOTS is over
+        const uint32_t slot = slot_ctr & (A_SLOTS - 1), sphase = (slot_ctr >> 2) & 1u;
+        mbar_wait(&a_free[slot], sphase ^ 1);
+        __syncwarp();
+        if (lane == 0) { if (rank == 0) mbar_arrive(&ready[slot]); else mbar_arrive_remote(ready_leader + slot * 8); }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ======================= epilogue warps (own 128 rows of C; L half, then R half) =======================
+    setmaxnreg_inc<L::REGS_EPI>();
+    const int ew = warp - 12;
+    const int q = warp & 3;
+    float* stg = epi_stage + ew * 32 * EPI_LD;
+    const bool masked = p.act == GTS_ACT_MASK_POS;
+    const uint32_t tmem_empty_leader = mapa_u32(smem_u32(&tmem_empty[0]), 0);
+    // fast path: full 32-row groups, the mask operand laid out like C
+    const bool fast_ok = !GTS_DBG(3) && (p.act != GTS_ACT_MASK_POS || p.ldaux == p.ldc);
+    uint32_t h = 0;
+    for (int w = cluster_id; w < n_work; w += n_clusters) {
+      const int m0 = (w / p.tiles_n) * (2 * BM) + (int)rank * BM + q * 32;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half, ++h) {
+        const uint32_t acc = h % 3u, full_phase = (h / 3u) & 1u;
+        const int n0 = (w % p.tiles_n) * (2 * L::BN_HALF) + half * L::BN_HALF;
+        const uint32_t t_base = tmem_base + acc * L::BN_HALF + ((uint32_t)(q * 32) << 16);
+        if (GTS_TR_ON && ew == 0) {
+          if (lane == 0) GTS_TR((int)(h >> 1), 8 + 3 * half, clock64());
+          mbar_wait(&tmem_full[acc], full_phase);
+          if (lane == 0) GTS_TR((int)(h >> 1), 9 + 3 * half, clock64());
+        }
+        if (fast_ok && m0 + 32 <= p.M) {
+          // whole slice into registers, accumulator released inside, stores afterwards
+          if (p.act == GTS_ACT_MASK_POS)
+            epilogue_half_regs<GTS_ACT_MASK_POS>(p, t_base, m0, n0, stg, lane, &tmem_full[acc], full_phase, &tmem_empty[acc],
+                                                 tmem_empty_leader + acc * 8, rank == 0);
+          else if (p.act == GTS_ACT_RELU)
+            epilogue_half_regs<GTS_ACT_RELU>(p, t_base, m0, n0, stg, lane, &tmem_full[acc], full_phase, &tmem_empty[acc],
+                                             tmem_empty_leader + acc * 8, rank == 0);
+          else
+            epilogue_half_regs<GTS_ACT_NONE>(p, t_base, m0, n0, stg, lane, &tmem_full[acc], full_phase, &tmem_empty[acc],
+                                             tmem_empty_leader + acc * 8, rank == 0);
+        } else {
+          // partial row group (last M tile) or a mask operand with its own leading dimension: generic chunk-wise path
+          epilogue_tile<false>(p, t_base, m0, n0, p.C, stg, lane, 0, 32, masked, &tmem_full[acc], full_phase);
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (rank == 0) mbar_arrive(&tmem_empty[acc]); else mbar_arrive_remote(tmem_empty_leader + acc * 8); }
+        }
+        if (GTS_TR_ON && ew == 0 && lane == 0) GTS_TR((int)(h >> 1), 10 + 3 * half, clock64());
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();                                // no CTA may exit (or free TMEM) while its peer still uses it
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -1385,6 +1916,36 @@ static int launch_ts2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtens
   return GTS_OK;
 }
 
+static long long* g_ntw_trace = nullptr;      // GTS_TRACE builds: set through gts_debug_set_trace
+#ifdef GTS_TRACE
+extern "C" GTS_API void gts_debug_set_trace(void* device_ptr) { g_ntw_trace = reinterpret_cast<long long*>(device_ptr); }
+static int g_dbg_flags_host = 0;
+extern "C" GTS_API void gts_debug_set_flags(int flags) { g_dbg_flags_host = flags; }
+#endif
+
+static int launch_ntw(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1, const CUtensorMap& b2,
+                      const Params& p, int n_work, cudaStream_t st) {
+  using L = NtwCfg;
+  static bool done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_x3ntw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::dyn_bytes);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d) failed: %s", L::dyn_bytes, cudaGetErrorString(e)); return GTS_ERR_CUDA; }
+    if (dev >= 0 && dev < 64) done[dev] = true;
+  }
+  const int pairs = sm_count() / 2;
+  const int grid = 2 * (n_work < pairs ? n_work : pairs);          // one CTA pair (cluster of 2) per TPC
+  Params q = p;
+  q.trace = g_ntw_trace;
+#ifdef GTS_TRACE
+  q.dbg = g_dbg_flags_host;
+#endif
+  gemm_x3ntw_kernel<<<grid, L::THREADS, L::dyn_bytes, st>>>(a1, a2, b1, b2, q);
+  GTS_LAUNCH_CHECK();
+  return GTS_OK;
+}
+
 // CTA-pair (cta_group::2) form for the wide shapes; GTS_X3_CTAS=1 keeps every shape on the one-CTA kernel
 static bool ts_pair_enabled() {
   static const bool off = getenv("GTS_X3_CTAS") && atoi(getenv("GTS_X3_CTAS")) == 1;
@@ -1436,6 +1997,12 @@ int gemm_nt_tcgen05(const gts_gemm_nt_args* a, cudaStream_t st) {
   p.BN = pair ? pick_bn(a->N, 64, Ts2Cfg::BN_MAX) : pick_bn(a->N, 16, in_tmem ? ts_bn_cap() : MAX_BN);
   p.tiles_m = pair ? (a->M + 2 * BM - 1) / (2 * BM) : (a->M + BM - 1) / BM;
   p.tiles_n = (a->N + p.BN - 1) / p.BN;
+  // 256-wide output tiles: one pass over A feeds both 128-column halves (gemm_x3ntw_kernel; GTS_X3_NTW=0 keeps the
+  // N = 128 pair kernel for A/B runs)
+  static const bool ntw_on = !(getenv("GTS_X3_NTW") && atoi(getenv("GTS_X3_NTW")) == 0);
+  static const int bf_cross = getenv("GTS_X3_BF16") ? atoi(getenv("GTS_X3_BF16")) : 1;    // bf16 cross terms: default on
+  const bool wide = pair && ntw_on && bf_cross == 1 && a->N % 256 == 0;
+  if (wide) p.tiles_n = a->N / 256;          // p.BN stays 128: the UMMA N of one half tile
   p.M = a->M; p.N = a->N; p.C = a->C; p.ldc = a->ldc;
   p.kb1 = (a->K1 + BK - 1) / BK;
   p.kb2 = two ? (a->K2 + BK - 1) / BK : 0;
@@ -1455,7 +2022,7 @@ int gemm_nt_tcgen05(const gts_gemm_nt_args* a, cudaStream_t st) {
   // cross terms of the 3xTF32 scheme as bf16 MMAs (8 instead of 12 MMAs per k-block; GTS_X3_BF16=0: all-TF32 form).
   // Measured: same error against fp64 (2.7e-6 max on K=256 products, logits 2.6e-5 on the 8-layer stack), K=256
   // 59.8 -> 55.9 us, K=512 100.6 -> 98.3 us, training step 5.19 -> 5.10 ms.
-  static const int bf_cross = getenv("GTS_X3_BF16") ? atoi(getenv("GTS_X3_BF16")) : 1;    // default on
+  if (wide) return launch_ntw(tA1, tA2, tB1, tB2, p, n_work, st);
   if (pair && bf_cross == 2) return launch_ts2<false, false, 2>(tA1, tA2, tB1, tB2, p, n_work, st);
   if (pair && bf_cross == 1) return launch_ts2<false, false, 1>(tA1, tA2, tB1, tB2, p, n_work, st);
   if (pair) return launch_ts2<false>(tA1, tA2, tB1, tB2, p, n_work, st);

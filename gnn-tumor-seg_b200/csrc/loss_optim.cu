@@ -24,6 +24,7 @@ __global__ void ce_weighted_kernel(const float* __restrict__ logits, int64_t ld,
     const bool valid = (y >= 0 && y < C);
     const float w = valid ? class_w[y] : 0.f;
     if (valid) { loss_part += w * (lse - z[y]); w_part += w; }
+    else if (y != -100) loss_part = __int_as_float(0x7fc00000);   // torch raises on such a label: poison the loss
     if (dlogits) {
 #pragma unroll 4
       for (int c = 0; c < C; ++c) {
@@ -76,6 +77,29 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
+// hyper = {lr, beta1, beta2, eps, weight_decay, step}: bias corrections from the device-side step count
+__global__ void adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, int64_t n, const float* __restrict__ hyper, float gscale,
+                                 const float* __restrict__ gdenom) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
+  const double step = (double)hyper[5];
+  const float bc1 = (float)(1.0 - pow((double)b1, step));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, step));
+  const float gs = gdenom ? gscale / *gdenom : gscale;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float grad = g[i] * gs;
+    float param = p[i] * (1.f - lr * wd);
+    const float mi = b1 * m[i] + (1.f - b1) * grad;
+    const float vi = b2 * v[i] + (1.f - b2) * grad * grad;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    param -= (lr / bc1) * (mi / denom);
+    p[i] = param;
+  }
+}
+__global__ void bump_step_kernel(float* hyper) { hyper[5] += 1.f; }
+
 static inline int ew_grid(int64_t n, int threads) {
   int64_t b = ceil_div<int64_t>(n, threads);
   const int64_t cap = (int64_t)sm_count() * 16;
@@ -122,6 +146,19 @@ int gts_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_a
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   adamw_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                                weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale, grad_denom);
+  GTS_LAUNCH_CHECK();
+  return GTS_OK;
+}
+
+int gts_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                       float* hyper, float grad_scale, const float* grad_denom, gts_stream_t stream) {
+  GTS_CHECK_ARG(n >= 0, "gts_adamw_step_dev: negative size");
+  GTS_CHECK_ARG(hyper, "gts_adamw_step_dev: null hyper-parameter block");
+  bump_step_kernel<<<1, 1, 0, as_stream(stream)>>>(hyper);
+  GTS_LAUNCH_CHECK();
+  if (n == 0) return GTS_OK;
+  GTS_CHECK_ARG(param && grad && exp_avg && exp_avg_sq, "gts_adamw_step_dev: null pointer");
+  adamw_dev_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, hyper, grad_scale, grad_denom);
   GTS_LAUNCH_CHECK();
   return GTS_OK;
 }

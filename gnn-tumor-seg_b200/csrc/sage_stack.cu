@@ -11,7 +11,7 @@ struct StackPlan {
   int L = 0;
   int64_t N = 0;
   size_t neigh[kMaxLayers], arg[kMaxLayers], out[kMaxLayers];
-  size_t P = 0, g0 = 0, g1 = 0, dP = 0, gemm_ws = 0, colsum_ws = 0;
+  size_t P = 0, g0 = 0, g1 = 0, dP = 0, gemm_ws = 0, colsum_ws = 0, dlogits = 0;
   size_t wnT[kMaxLayers], wsT[kMaxLayers], wpT[kMaxLayers];      // transposed weights of every layer (one batched launch)
   size_t gemm_ws_bytes = 0, colsum_ws_bytes = 0;
   size_t total = 0;
@@ -57,6 +57,7 @@ static bool make_plan(const gts_sage_layer* layers, int L, int64_t N, bool train
     pl.gemm_ws_bytes = gw; pl.colsum_ws_bytes = cw;
     pl.gemm_ws = take(gw);
     pl.colsum_ws = take(cw);
+    pl.dlogits = take(n * layers[L - 1].dout * 4);     // gts_sage_step: gradient of the loss w.r.t. the logits
   } else {
     pl.P = take(n * max_din * 4);
     pl.neigh[0] = take(n * max_din * 4);      // single reused neigh buffer
@@ -140,13 +141,21 @@ int gts_sage_forward(const gts_sage_layer* layers, int32_t n_layers,
   return GTS_OK;
 }
 
-int gts_sage_backward(const gts_sage_layer* layers, const gts_sage_layer_grads* grads, int32_t n_layers,
-                      const int32_t* csc_indptr, const int32_t* csc_indices, int32_t n_nodes,
-                      const float* feats, int64_t ldf, const float* dlogits, int64_t ldd,
-                      float* dfeats, int64_t lddf,
-                      void* workspace, size_t workspace_bytes, int32_t mode, gts_stream_t stream) {
+// Layers layer_hi-1 .. layer_lo of the backward pass.  The gradient that enters layer l (dZ) lives at a fixed place:
+// dlogits for the top layer, otherwise the ping-pong buffer (L-2-l) & 1 of the workspace — so consecutive range calls
+// continue each other (the data-parallel trainer all-reduces the finished layers' gradients in between).
+static int backward_range(const gts_sage_layer* layers, const gts_sage_layer_grads* grads, int32_t n_layers,
+                          int32_t layer_hi, int32_t layer_lo,
+                          const int32_t* csc_indptr, const int32_t* csc_indices, int32_t n_nodes,
+                          const float* feats, int64_t ldf, const float* dlogits, int64_t ldd,
+                          float* dfeats, int64_t lddf,
+                          void* workspace, size_t workspace_bytes, int32_t mode, gts_stream_t stream) {
   GTS_CHECK_ARG(layers && grads && n_layers >= 1, "gts_sage_backward: no layers");
   GTS_CHECK_ARG(n_nodes >= 0, "gts_sage_backward: negative n_nodes");
+  GTS_CHECK_ARG(0 <= layer_lo && layer_lo <= layer_hi && layer_hi <= n_layers, "gts_sage_backward: bad layer range [%d,%d)", layer_lo, layer_hi);
+  // the gradient handed in is taken as the gradient of the top layer's OUTPUT: a ReLU there would need its mask,
+  // which this entry point does not see (the reference's top layer has no activation, model/networks.py:30)
+  GTS_CHECK_ARG(!layers[n_layers - 1].relu, "gts_sage_backward: a ReLU on the last layer is not supported (apply its mask to dlogits and clear the flag)");
   StackPlan pl;
   GTS_CHECK_ARG(make_plan(layers, n_layers, n_nodes, true, mode, pl), "gts_sage_backward: inconsistent layer dims");
   if (n_nodes > 0 && workspace_bytes < pl.total) {
@@ -155,10 +164,7 @@ int gts_sage_backward(const gts_sage_layer* layers, const gts_sage_layer_grads* 
   }
   GTS_CHECK_ARG(n_nodes == 0 || (feats && dlogits && workspace), "gts_sage_backward: null pointer");
   const int N = n_nodes;
-  const float* dZ = dlogits;
-  int64_t ldz = ldd;
-  int pp = 0;
-  // every weight transpose of the pass (data-gradient GEMMs consume K-major B operands) in launches of <= 96 jobs
+  // every weight transpose of the range (data-gradient GEMMs consume K-major B operands) in launches of <= 96 jobs
   {
     TransposeBatch tb;
     auto push = [&](const float* in, int rows, int cols, size_t off) -> int {
@@ -166,7 +172,7 @@ int gts_sage_backward(const gts_sage_layer* layers, const gts_sage_layer_grads* 
       tb.job[tb.n++] = TransposeJob{in, at(workspace, off), cols, rows, rows, cols};
       return GTS_OK;
     };
-    for (int l = 0; l < n_layers && N > 0; ++l) {
+    for (int l = layer_lo; l < layer_hi && N > 0; ++l) {
       const gts_sage_layer& ly = layers[l];
       GTS_CHECK_ARG(ly.Wp && ly.Ws && ly.Wn, "gts_sage_backward: layer %d has a null weight", l);
       GTS_TRY(push(ly.Wn, ly.dout, ly.din, pl.wnT[l]));
@@ -175,12 +181,15 @@ int gts_sage_backward(const gts_sage_layer* layers, const gts_sage_layer_grads* 
         GTS_TRY(push(ly.Wp, ly.din, ly.din, pl.wpT[l]));
       }
     }
-    GTS_TRY(launch_transpose_batch(tb, as_stream(stream)));
+    if (tb.n > 0) GTS_TRY(launch_transpose_batch(tb, as_stream(stream)));
   }
-  for (int l = n_layers - 1; l >= 0; --l) {
+  for (int l = layer_hi - 1; l >= layer_lo; --l) {
     const gts_sage_layer& ly = layers[l];
     const gts_sage_layer_grads& g = grads[l];
     GTS_CHECK_ARG(g.dWp && g.dbp && g.dWs && g.dWn && g.db, "gts_sage_backward: layer %d has a null gradient pointer", l);
+    const float* dZ = dlogits;
+    int64_t ldz = ldd;
+    if (l + 1 < n_layers) { dZ = at(workspace, ((n_layers - 2 - l) & 1) ? pl.g1 : pl.g0); ldz = ly.dout; }
     const float* h = (l == 0) ? feats : at(workspace, pl.out[l - 1]);
     const int64_t ldh = (l == 0) ? ldf : ly.din;
     const float* neigh = at(workspace, pl.neigh[l]);
@@ -190,6 +199,8 @@ int gts_sage_backward(const gts_sage_layer* layers, const gts_sage_layer_grads* 
     // dWs = dZ^T h, dWn = dZ^T neigh and db = column sums of dZ: one pass over dZ in the 3xTF32 mode
     GTS_TRY(gts_gemm_tn2_colsum(dZ, ldz, h, ldh, neigh, ly.din, g.dWs, g.dWn, ly.din, ly.dout, ly.din, N, mode, g.db, gws,
                                 pl.gemm_ws_bytes, stream));
+    if (g.db2 && N > 0)      // fc_neigh.bias enters the output as fc_self.bias does: same gradient, its own arena slot
+      GTS_CUDA(cudaMemcpyAsync(g.db2, g.db, sizeof(float) * (size_t)ly.dout, cudaMemcpyDeviceToDevice, as_stream(stream)));
     // dNeigh' = (dZ Wn) * (neigh > 0)
     const float* WnT = at(workspace, pl.wnT[l]);
     // Measured (profiles/r01_gemm_x3_pipeline.md): routing the masked tile through the arg-max from inside the GEMM
@@ -210,15 +221,66 @@ int gts_sage_backward(const gts_sage_layer* layers, const gts_sage_layer_grads* 
       float* dh;
       int64_t lddh;
       if (l == 0) { dh = dfeats; lddh = lddf; }
-      else { dh = at(workspace, pp ? pl.g1 : pl.g0); lddh = ly.din; }
+      else { dh = at(workspace, ((n_layers - 1 - l) & 1) ? pl.g1 : pl.g0); lddh = ly.din; }
       // dh = (dZ Ws + dP' Wp) * (h > 0): h is the ReLU output of layer l-1 (no mask for the input features)
       const bool mask = l > 0 && layers[l - 1].relu != 0;
       GTS_TRY(nt(dZ, ldz, ly.dout, WsT, ly.dout, dP, ly.din, ly.din, WpT, ly.din, nullptr,
                  mask ? GTS_ACT_MASK_POS : GTS_ACT_NONE, mask ? h : nullptr, ldh, dh, lddh, N, ly.din, mode, stream));
-      dZ = dh; ldz = lddh; pp ^= 1;
     }
   }
   return GTS_OK;
+}
+
+int gts_sage_backward(const gts_sage_layer* layers, const gts_sage_layer_grads* grads, int32_t n_layers,
+                      const int32_t* csc_indptr, const int32_t* csc_indices, int32_t n_nodes,
+                      const float* feats, int64_t ldf, const float* dlogits, int64_t ldd,
+                      float* dfeats, int64_t lddf,
+                      void* workspace, size_t workspace_bytes, int32_t mode, gts_stream_t stream) {
+  return backward_range(layers, grads, n_layers, n_layers, 0, csc_indptr, csc_indices, n_nodes, feats, ldf, dlogits, ldd,
+                        dfeats, lddf, workspace, workspace_bytes, mode, stream);
+}
+
+int gts_sage_backward_range(const gts_sage_layer* layers, const gts_sage_layer_grads* grads, int32_t n_layers,
+                            int32_t layer_hi, int32_t layer_lo,
+                            const int32_t* csc_indptr, const int32_t* csc_indices, int32_t n_nodes,
+                            const float* feats, int64_t ldf, const float* dlogits, int64_t ldd,
+                            float* dfeats, int64_t lddf,
+                            void* workspace, size_t workspace_bytes, int32_t mode, gts_stream_t stream) {
+  return backward_range(layers, grads, n_layers, layer_hi, layer_lo, csc_indptr, csc_indices, n_nodes, feats, ldf, dlogits,
+                        ldd, dfeats, lddf, workspace, workspace_bytes, mode, stream);
+}
+
+int gts_sage_step(const gts_sage_step_args* a, gts_stream_t stream) {
+  GTS_CHECK_ARG(a && a->layers && a->grads && a->n_layers >= 1, "gts_sage_step: no layers");
+  GTS_CHECK_ARG(a->n_nodes >= 1, "gts_sage_step: empty batch");
+  GTS_CHECK_ARG(a->labels && a->class_w && a->sums && a->logits && a->workspace, "gts_sage_step: null pointer");
+  GTS_CHECK_ARG(0 <= a->bwd_layer_lo && a->bwd_layer_lo <= a->n_layers, "gts_sage_step: bad bwd_layer_lo");
+  StackPlan pl;
+  GTS_CHECK_ARG(make_plan(a->layers, a->n_layers, a->n_nodes, true, a->mode, pl), "gts_sage_step: inconsistent layer dims");
+  if (a->workspace_bytes < pl.total) {
+    set_error("gts_sage_step: workspace %zu < required %zu", a->workspace_bytes, pl.total);
+    return GTS_ERR_WORKSPACE;
+  }
+  const int C = a->layers[a->n_layers - 1].dout;
+  float* dlogits = at(a->workspace, pl.dlogits);
+  GTS_TRY(gts_sage_forward(a->layers, a->n_layers, a->indptr, a->indices, a->n_nodes, a->feats, a->ldf, a->logits, a->ldl,
+                           a->workspace, a->workspace_bytes, 1, a->mode, stream));
+  GTS_CUDA(cudaMemsetAsync(a->sums, 0, 2 * sizeof(float), as_stream(stream)));
+  GTS_TRY(gts_ce_weighted(a->logits, a->ldl, a->labels, a->class_w, a->n_nodes, C, a->sums, dlogits, C, stream));
+  if (a->normalize)      // gradients of the weighted MEAN (model/gnn_model.py:30,42): d/dz of sum(w nll) / sum(w)
+    GTS_TRY(gts_scale_by_inv(dlogits, (int64_t)a->n_nodes * C, 1.0f, a->sums + 1, stream));
+  return backward_range(a->layers, a->grads, a->n_layers, a->n_layers, a->bwd_layer_lo, a->csc_indptr, a->csc_indices,
+                        a->n_nodes, a->feats, a->ldf, dlogits, C, nullptr, 0, a->workspace, a->workspace_bytes, a->mode, stream);
+}
+
+int gts_sage_step_backward_rest(const gts_sage_step_args* a, int32_t layer_hi, int32_t layer_lo, gts_stream_t stream) {
+  GTS_CHECK_ARG(a && a->layers && a->grads && a->n_layers >= 1, "gts_sage_step_backward_rest: no layers");
+  StackPlan pl;
+  GTS_CHECK_ARG(make_plan(a->layers, a->n_layers, a->n_nodes, true, a->mode, pl), "gts_sage_step_backward_rest: inconsistent layer dims");
+  const int C = a->layers[a->n_layers - 1].dout;
+  return backward_range(a->layers, a->grads, a->n_layers, layer_hi, layer_lo, a->csc_indptr, a->csc_indices, a->n_nodes,
+                        a->feats, a->ldf, at(a->workspace, pl.dlogits), C, nullptr, 0, a->workspace, a->workspace_bytes,
+                        a->mode, stream);
 }
 
 }  // extern "C"

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 from torch.utils.data import DataLoader
 
-from . import ops
+from . import evaluation, ops
 from ._lib import GtsError
 from .data_loader import DevicePrefetcher
 from .graph import minibatch_graphs
@@ -32,12 +32,6 @@ class WeightedCrossEntropy(torch.nn.Module):
 
     def forward(self, logits, labels):
         return ops.weighted_cross_entropy(logits, labels, self.weight)
-
-
-def _dice(pred, true, cls):
-    p, t = pred == cls, true == cls
-    denom = p.sum() + t.sum()
-    return float(2.0 * (p & t).sum() / denom) if denom > 0 else float("nan")
 
 
 class GNN:
@@ -80,7 +74,7 @@ class GNN:
         base = getattr(dataset, "dataset", dataset)
         assert getattr(base, "read_label", True) == True
         self.net.eval()
-        # metrics: loss, 3 node dices, 3 voxel dices, 3 voxel hausdorff (HD95 is out of scope -> nan)
+        # metrics: loss, 3 node dices (WT, CT, ET), 3 voxel dices, 3 voxel HD95
         metrics = np.zeros((len(dataset), 10))
         counts = np.zeros((len(dataset), 8))
         i = 0
@@ -104,16 +98,19 @@ class GNN:
         return avg_metrics, total_counts
 
     def calculate_all_metrics_for_brain(self, mri_id, dataset, node_preds, node_labels):
-        label_counts = np.concatenate([np.bincount(node_preds, minlength=4)[:4], np.bincount(node_labels, minlength=4)[:4]])
-        # BraTS regions on the reference's internal labels: WT = !=0, TC = {2,3}... kept simple: per-class Dice 1..3
-        node_dices = np.array([_dice(node_preds, node_labels, c) for c in (1, 2, 3)])
+        """model/gnn_model.py:76-87: label counts (predicted, true), node-wise WT/CT/ET Dice, voxel-wise WT/CT/ET
+        Dice and HD95 with the reference's definitions (gnn_tumor_seg_b200.evaluation, pinned to outputs of the
+        reference's model/evaluation.py).  The projection to voxels runs on the device (K7).  A dataset without
+        voxel accessors (in-memory lists of graphs) yields nan in the six voxel slots instead of raising."""
+        label_counts = np.concatenate([evaluation.count_node_labels(node_preds), evaluation.count_node_labels(node_labels)])
+        node_dices = evaluation.calculate_node_dices(node_preds, node_labels)
         voxel_metrics = np.full(6, np.nan)
         base = getattr(dataset, "dataset", dataset)
         if hasattr(base, "get_supervoxel_partitioning") and hasattr(base, "get_voxel_labels"):
             sv_partitioning = base.get_supervoxel_partitioning(mri_id)
             true_voxels = base.get_voxel_labels(mri_id)
             pred_voxels = project_nodes_to_img(sv_partitioning, node_preds)
-            voxel_metrics[:3] = [_dice(pred_voxels, true_voxels, c) for c in (1, 2, 3)]
+            voxel_metrics = evaluation.calculate_brats_metrics(pred_voxels, true_voxels)
         return label_counts, np.concatenate([node_dices, voxel_metrics])
 
     def save_weights(self, folder, name):

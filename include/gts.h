@@ -218,6 +218,7 @@ typedef struct gts_sage_layer {
 
 typedef struct gts_sage_layer_grads {
   float* dWp; float* dbp; float* dWs; float* dWn; float* db;
+  float* db2;   /* nullable: second copy of db (gradient of fc_neigh.bias when the module keeps both DGL<=0.7 biases) */
 } gts_sage_layer_grads;
 
 /* Workspace for n_nodes nodes.  training != 0 keeps every layer's neigh /
@@ -241,13 +242,50 @@ GTS_API int gts_sage_backward(const gts_sage_layer* layers, const gts_sage_layer
                       float* dfeats, int64_t lddf,
                       void* workspace, size_t workspace_bytes, int32_t mode, gts_stream_t stream);
 
+/* Layers layer_hi-1 .. layer_lo of gts_sage_backward.  The gradient entering layer l is kept at a fixed place of the
+ * workspace, so consecutive calls [L,k) then [k,0) equal one gts_sage_backward: the data-parallel trainer
+ * all-reduces the gradients of the finished layers on a side stream in between. */
+GTS_API int gts_sage_backward_range(const gts_sage_layer* layers, const gts_sage_layer_grads* grads, int32_t n_layers,
+                            int32_t layer_hi, int32_t layer_lo,
+                            const int32_t* csc_indptr, const int32_t* csc_indices, int32_t n_nodes,
+                            const float* feats, int64_t ldf, const float* dlogits, int64_t ldd,
+                            float* dfeats, int64_t lddf,
+                            void* workspace, size_t workspace_bytes, int32_t mode, gts_stream_t stream);
+
+/* One training step of GNN.run_epoch's loop body minus the optimiser (model/gnn_model.py:41-45) as ONE host call:
+ * logits = GraphSage.forward; sums = [sum w*nll, sum w] (zeroed by the call; loss = sums[0]/sums[1]);
+ * gradients of every layer >= bwd_layer_lo into grads (normalize != 0: of the weighted MEAN, the reference's loss;
+ * normalize == 0: of the un-normalised sum, for data-parallel training where the denominator is global).
+ * All scratch incl. d(loss)/d(logits) lives in the caller's workspace (gts_sage_workspace_bytes, training = 1);
+ * nothing is allocated, nothing synchronises: the call can be captured into a CUDA graph. */
+typedef struct gts_sage_step_args {
+  const gts_sage_layer* layers; const gts_sage_layer_grads* grads; int32_t n_layers;
+  int32_t n_nodes;
+  const int32_t* indptr; const int32_t* indices;           /* in-edge CSR */
+  const int32_t* csc_indptr; const int32_t* csc_indices;   /* nullable: deterministic arg-max backward */
+  const float* feats; int64_t ldf;
+  const int64_t* labels; const float* class_w;
+  float* sums;                  /* device float[2] */
+  float* logits; int64_t ldl;   /* out: [n_nodes, dout_last] */
+  void* workspace; size_t workspace_bytes;
+  int32_t mode;                 /* gts_gemm_mode */
+  int32_t normalize;
+  int32_t bwd_layer_lo;         /* 0: whole backward; k > 0: stop after layer k (continue with gts_sage_step_backward_rest) */
+  int32_t reserved;
+} gts_sage_step_args;
+GTS_API int gts_sage_step(const gts_sage_step_args* args, gts_stream_t stream);
+/* Backward layers layer_hi-1 .. layer_lo of a step started with bwd_layer_lo = layer_hi. */
+GTS_API int gts_sage_step_backward_rest(const gts_sage_step_args* args, int32_t layer_hi, int32_t layer_lo, gts_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * K8 — weighted-mean cross entropy (model/gnn_model.py:30,42).
  * ------------------------------------------------------------------------ */
 
 /* sums[0] += sum_i w[y_i]*nll_i ; sums[1] += sum_i w[y_i]  (caller zeroes sums);
  * dlogits[i,c] = w[y_i]*(softmax(z_i)[c] - [c==y_i])   (NOT yet divided by
- * sums[1]; nullable).  labels are int64 as torch.LongTensor. */
+ * sums[1]; nullable).  labels are int64 as torch.LongTensor; label -100 (torch's
+ * ignore_index) contributes nothing; any other label outside [0, n_classes) — where
+ * torch raises — poisons sums[0] with NaN, so the loss cannot silently look fine. */
 GTS_API int gts_ce_weighted(const float* logits, int64_t ld, const int64_t* labels, const float* class_w,
                     int32_t n_nodes, int32_t n_classes, float* sums, float* dlogits, int64_t ldd,
                     gts_stream_t stream);
@@ -367,6 +405,13 @@ GTS_API int gts_gat_attn_grad2(const float* Z, int64_t ldz, const float* coef_l,
 GTS_API int gts_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                    float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
                    float grad_scale, const float* grad_denom, gts_stream_t stream);
+
+/* Same update with the hyper-parameters read on the DEVICE, for steps replayed from a CUDA graph:
+ * hyper = device float[8] {lr, beta1, beta2, eps, weight_decay, step, 0, 0}; hyper[5] (the step count,
+ * exact in fp32 up to 2^24) is incremented by the call before use; ExponentialLR = the host rewriting hyper[0]
+ * between replays (model/gnn_model.py:29,47). */
+GTS_API int gts_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                       float* hyper, float grad_scale, const float* grad_denom, gts_stream_t stream);
 
 #ifdef __cplusplus
 }
