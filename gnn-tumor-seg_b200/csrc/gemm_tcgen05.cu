@@ -161,6 +161,26 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Explicit shared-state-space accesses.  Through generic pointers (uint8_t* smem + offset) the compiler emitted generic
+// LD.E / ST.E for every tile access of the split and epilogue warps (63-79 per kernel in round 1's SASS, against 5-9
+// LDS / STS): generic accesses take the slower address path and queue behind outstanding global loads.
+__device__ __forceinline__ void sts_128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts_128f(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds_128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds_32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 // Shared-memory matrix descriptor (SM100 UMMA), version 1.
 //   K-major  (layout 2 = SWIZZLE_128B, 16-byte swizzle granule): LBO unused (1),
 //            SBO = 1024 B between 8-row groups;
@@ -246,6 +266,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t t_base, 
                                               uint32_t full_phase) {
   const int cc = (lane & 7) * 4;
   const int rsub = lane >> 3;
+  const uint32_t stg_u = smem_u32(stg);
   // ReLU-mask source: fetched one chunk ahead so its latency hides behind the TMEM load
   float4 aux_cur[8], aux_nxt[8];
   auto load_aux = [&](int c0, float4 (&dst)[8]) {
@@ -270,9 +291,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t t_base, 
     // lane = row: park the 32 columns of this row in the padded staging tile
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * j) =
-          make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                      __uint_as_float(v[4 * j + 3]));
+      sts_128(stg_u + (uint32_t)(lane * EPI_LD + 4 * j) * 4, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     __syncwarp();
     // coalesced write-out: 8 lanes cover one 128-byte row segment, 4 rows per instruction
     const int col = n0 + c0 + cc;
@@ -288,7 +307,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t t_base, 
       const int rr = 4 * j + rsub;
       const int64_t row = (int64_t)m0 + rr;
       if (row < p.M && col_ok) {
-        float4 x = *reinterpret_cast<const float4*>(stg + rr * EPI_LD + cc);
+        float4 x = lds_128(stg_u + (uint32_t)(rr * EPI_LD + cc) * 4);
         if (!TN) {
           x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
           if (p.act == GTS_ACT_RELU) {
@@ -470,8 +489,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         float4* lo = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES + OPER_BYTES);
 #pragma unroll 4
         for (int i = t; i < n_vec; i += L::SPLIT_WARPS * 32) {
-          const float4 x = hi[i];
-          lo[i] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+          const float4 x = lds_128(smem_u32(hi) + (uint32_t)i * 16);
+          sts_128f(smem_u32(lo) + (uint32_t)i * 16, make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w)));
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
         mbar_arrive(&split_bar[stage]);
@@ -690,21 +709,21 @@ gemm_x3ts_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         uint32_t hi[32], lo[32];
         if (!TN) {
           // K-major tile, 128B swizzle: row r at r * 128, 16-byte chunk c stored at chunk c ^ (r & 7)
-          const uint8_t* row = sa + r * 128;
+          const uint32_t row = smem_u32(sa) + (uint32_t)r * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            const float4 x = *reinterpret_cast<const float4*>(row + ((c ^ (r & 7)) << 4));
+            const float4 x = lds_128(row + ((uint32_t)(c ^ (r & 7)) << 4));
             hi[4 * c + 0] = __float_as_uint(x.x); hi[4 * c + 1] = __float_as_uint(x.y);
             hi[4 * c + 2] = __float_as_uint(x.z); hi[4 * c + 3] = __float_as_uint(x.w);
           }
         } else {
           // MN-major boxes [32 node rows][32 features], SWIZZLE_128B_ATOM_32B: box q holds this warp's 32
           // features; node row k at k * 128, 32-byte unit u stored at unit u ^ (k & 3)
-          const uint8_t* box = sa + q * 4096 + (lane & 7) * 4;
+          const uint32_t box = smem_u32(sa) + (uint32_t)(q * 4096 + (lane & 7) * 4);
           const int u = lane >> 3;
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
-            const float x = *reinterpret_cast<const float*>(box + k * 128 + ((u ^ (k & 3)) << 5));
+            const float x = lds_32(box + (uint32_t)(k * 128 + ((u ^ (k & 3)) << 5)));
             hi[k] = __float_as_uint(x);
             csum += x;
           }
@@ -739,8 +758,8 @@ gemm_x3ts_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         float4* lo = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES + A_STAGE_BYTES + L::B_BYTES);
 #pragma unroll 4
         for (int i = t; i < n_vec; i += 128) {
-          const float4 x = hi[i];
-          lo[i] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+          const float4 x = lds_128(smem_u32(hi) + (uint32_t)i * 16);
+          sts_128f(smem_u32(lo) + (uint32_t)i * 16, make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w)));
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
         mbar_arrive(&b_ready[stage]);
@@ -1154,21 +1173,21 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
           uint32_t hi[32], lo[32];
           if (!TN) {
             // K-major tile, 128B swizzle: row r at r * 128, 16-byte chunk c stored at chunk c ^ (r & 7)
-            const uint8_t* row = sa + r * 128;
+            const uint32_t row = smem_u32(sa) + (uint32_t)r * 128;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              const float4 x = *reinterpret_cast<const float4*>(row + ((c ^ (r & 7)) << 4));
+              const float4 x = lds_128(row + ((uint32_t)(c ^ (r & 7)) << 4));
               hi[4 * c + 0] = __float_as_uint(x.x); hi[4 * c + 1] = __float_as_uint(x.y);
               hi[4 * c + 2] = __float_as_uint(x.z); hi[4 * c + 3] = __float_as_uint(x.w);
             }
           } else {
             // MN-major boxes [32 node rows][32 features], SWIZZLE_128B_ATOM_32B: box q holds this warp's 32
             // features; node row k at k * 128, 32-byte unit u stored at unit u ^ (k & 3)
-            const uint8_t* box = sa + q * 4096 + (lane & 7) * 4;
+            const uint32_t box = smem_u32(sa) + (uint32_t)(q * 4096 + (lane & 7) * 4);
             const int u = lane >> 3;
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
-              const float x = *reinterpret_cast<const float*>(box + k * 128 + ((u ^ (k & 3)) << 5));
+              const float x = lds_32(box + (uint32_t)(k * 128 + ((u ^ (k & 3)) << 5)));
               hi[k] = __float_as_uint(x);
               csum += x;
             }
@@ -1238,7 +1257,8 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
                 // bf16(B) into chunk d and bf16(B_lo) into chunk 4 + d of the same row of the second tile
                 for (int i = t; i < half_bn * 4; i += 128) {
                   const int n = i >> 2, d = i & 3, sw = n & 7;
-                  const float4 x = hi[n * 8 + ((2 * d) ^ sw)], y = hi[n * 8 + ((2 * d + 1) ^ sw)];
+                  const float4 x = lds_128(smem_u32(hi) + (uint32_t)(n * 8 + ((2 * d) ^ sw)) * 16);
+                  const float4 y = lds_128(smem_u32(hi) + (uint32_t)(n * 8 + ((2 * d + 1) ^ sw)) * 16);
                   const float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
                   uint32_t hb[4], lb[4];
 #pragma unroll
@@ -1248,15 +1268,15 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
                     lb[e] = pack_bf16x2(a0 - __uint_as_float(__float_as_uint(a0) & 0xFFFFE000u),
                                         a1 - __uint_as_float(__float_as_uint(a1) & 0xFFFFE000u));
                   }
-                  uint4* row = reinterpret_cast<uint4*>(lo) + n * 8;
-                  row[d ^ sw] = make_uint4(hb[0], hb[1], hb[2], hb[3]);
-                  row[(4 + d) ^ sw] = make_uint4(lb[0], lb[1], lb[2], lb[3]);
+                  const uint32_t orow = smem_u32(lo) + (uint32_t)n * 128;
+                  sts_128(orow + (uint32_t)(d ^ sw) * 16, hb[0], hb[1], hb[2], hb[3]);
+                  sts_128(orow + (uint32_t)((4 + d) ^ sw) * 16, lb[0], lb[1], lb[2], lb[3]);
                 }
               } else {
 #pragma unroll 4
               for (int i = t; i < n_vec; i += 128) {
-                const float4 x = hi[i];
-                lo[i] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+                const float4 x = lds_128(smem_u32(hi) + (uint32_t)i * 16);
+                sts_128f(smem_u32(lo) + (uint32_t)i * 16, make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w)));
               }
               }
             }
@@ -1323,15 +1343,6 @@ __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.
 // Row pointers are formed once, chunk offsets are immediates, bias is fetched before the accumulator wait, the
 // ReLU-mask operand is fetched one chunk ahead row by row (no second register set).
 // ACT: GTS_ACT_NONE / GTS_ACT_RELU (bias, bias2 optional) / GTS_ACT_MASK_POS (aux with ldaux == ldc, no bias).
-__device__ __forceinline__ void sts_128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ float4 lds_128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-
 template <int ACT>
 __device__ __forceinline__ void epilogue_half_regs(const Params& p, uint32_t t_base, int m0, int n0, float* stg, int lane,
                                                    uint64_t* full_bar, uint32_t full_phase, uint64_t* empty_local,
