@@ -186,10 +186,20 @@ def check(rc: int, what: str = "") -> None:
 
 def require_cuda(*tensors) -> None:
     """Fail loudly if a tensor is not on a CUDA device (no CPU path exists)."""
+    import torch
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise GtsError("gnn_tumor_seg_b200 computes only on a CUDA device (B200, sm_100a); "
                            f"got a tensor on {t.device}. Move inputs with .to('cuda').")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        # launches go to the CURRENT device's current stream: a tensor of another GPU would fault there
+        if t.device.index is not None and t.device.index != cur:
+            raise GtsError(f"tensor on {t.device} but the current CUDA device is cuda:{cur}: wrap the call in "
+                           f"torch.cuda.device({t.device.index}) (one process per GPU is the supported layout)")
 
 
 def stream_ptr() -> int:

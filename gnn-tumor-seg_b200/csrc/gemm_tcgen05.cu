@@ -1871,16 +1871,25 @@ static bool encode_2d(CUtensorMap* tm, const float* base, int64_t rows, int64_t 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline bool operand_ok(const float* p, int64_t ld) { return p && al16(p) && ld % 4 == 0 && ld > 0; }
 
-template <bool TN, bool X3>
-static int configure_kernel() {
-  static bool done = false;
-  if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<TN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg<X3>::dyn_bytes);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d) failed: %s", Cfg<X3>::dyn_bytes, cudaGetErrorString(e)); return GTS_ERR_CUDA; }
-    done = true;
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember it per device ordinal (a process
+// that drives several GPUs, or switches the current device, must set it on each).
+constexpr int kMaxDevices = 64;
+template <typename Kernel>
+static int ensure_dyn_smem(Kernel kernel, int bytes, bool (&done)[kMaxDevices]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = -1;
+  if (dev < 0 || dev >= kMaxDevices || !done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d) failed: %s", bytes, cudaGetErrorString(e)); return GTS_ERR_CUDA; }
+    if (dev >= 0 && dev < kMaxDevices) done[dev] = true;
   }
   return GTS_OK;
+}
+
+template <bool TN, bool X3>
+static int configure_kernel() {
+  static bool done[kMaxDevices] = {};
+  return ensure_dyn_smem(gemm_tc_kernel<TN, X3>, Cfg<X3>::dyn_bytes, done);
 }
 
 template <bool TN, bool X3>
@@ -1898,12 +1907,8 @@ template <bool TN, int BNC>
 static int launch_ts(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1, const CUtensorMap& b2,
                      const Params& p, int n_work, cudaStream_t st) {
   using L = TsCfg<BNC>;
-  static bool done = false;
-  if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_x3ts_kernel<TN, BNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::dyn_bytes);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d) failed: %s", L::dyn_bytes, cudaGetErrorString(e)); return GTS_ERR_CUDA; }
-    done = true;
-  }
+  static bool done[kMaxDevices] = {};
+  if (int rc = ensure_dyn_smem(gemm_x3ts_kernel<TN, BNC>, L::dyn_bytes, done)) return rc;
   const int grid = n_work < sm_count() ? n_work : sm_count();
   gemm_x3ts_kernel<TN, BNC><<<grid, L::THREADS, L::dyn_bytes, st>>>(a1, a2, b1, b2, p);
   GTS_LAUNCH_CHECK();
@@ -1914,12 +1919,8 @@ template <bool TN, bool DUAL = false, int BF = 0>
 static int launch_ts2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1, const CUtensorMap& b2,
                       const Params& p, int n_work, cudaStream_t st) {
   using L = Ts2CfgT<DUAL, BF>;
-  static bool done = false;
-  if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_x3ts2_kernel<TN, DUAL, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::dyn_bytes);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d) failed: %s", L::dyn_bytes, cudaGetErrorString(e)); return GTS_ERR_CUDA; }
-    done = true;
-  }
+  static bool done[kMaxDevices] = {};
+  if (int rc = ensure_dyn_smem(gemm_x3ts2_kernel<TN, DUAL, BF>, L::dyn_bytes, done)) return rc;
   const int pairs = sm_count() / 2;
   const int grid = 2 * (n_work < pairs ? n_work : pairs);          // one CTA pair (cluster of 2) per TPC
   gemm_x3ts2_kernel<TN, DUAL, BF><<<grid, L::THREADS, L::dyn_bytes, st>>>(a1, a2, b1, b2, p);
@@ -1937,14 +1938,8 @@ extern "C" GTS_API void gts_debug_set_flags(int flags) { g_dbg_flags_host = flag
 static int launch_ntw(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1, const CUtensorMap& b2,
                       const Params& p, int n_work, cudaStream_t st) {
   using L = NtwCfg;
-  static bool done[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_x3ntw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::dyn_bytes);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d) failed: %s", L::dyn_bytes, cudaGetErrorString(e)); return GTS_ERR_CUDA; }
-    if (dev >= 0 && dev < 64) done[dev] = true;
-  }
+  static bool done[kMaxDevices] = {};
+  if (int rc = ensure_dyn_smem(gemm_x3ntw_kernel, L::dyn_bytes, done)) return rc;
   const int pairs = sm_count() / 2;
   const int grid = 2 * (n_work < pairs ? n_work : pairs);          // one CTA pair (cluster of 2) per TPC
   Params q = p;

@@ -19,6 +19,7 @@ from .data_loader import DevicePrefetcher
 from .graph import minibatch_graphs
 from .networks import init_graph_net
 from .project import project_nodes_to_img
+from .trainer import FusedAdamW, SageTrainer
 
 BATCH_SIZE = 6          # model/gnn_model.py:12
 
@@ -43,8 +44,16 @@ class GNN:
         class_weights = torch.FloatTensor(hyperparameters.class_weights).to(self.device)
         self.net = init_graph_net(model_type, hyperparameters)
         self.net.to(self.device)
-        self.optimizer = torch.optim.AdamW(self.net.parameters(), lr=hyperparameters.lr,
-                                           weight_decay=hyperparameters.w_decay)
+        # AdamW as one kernel over a flat parameter arena (gts_adamw_step_dev); a torch.optim.Optimizer, so the
+        # reference's ExponentialLR drives it unchanged (model/gnn_model.py:28-29).  GraphSage('pool') without
+        # dropout trains through the one-call step (trainer.SageTrainer: forward + CE + backward in gts_sage_step);
+        # every other network through autograd + the same optimiser.
+        self.trainer = None
+        try:
+            self.trainer = SageTrainer(self.net, class_weights, lr=hyperparameters.lr, weight_decay=hyperparameters.w_decay)
+            self.optimizer = self.trainer.optimizer
+        except GtsError:
+            self.optimizer = FusedAdamW(self.net.parameters(), lr=hyperparameters.lr, weight_decay=hyperparameters.w_decay)
         self.lr_decay = torch.optim.lr_scheduler.ExponentialLR(self.optimizer, hyperparameters.lr_decay, last_epoch=-1)
         self.loss_fcn = WeightedCrossEntropy(class_weights)
         self.train_loader = DataLoader(train_dataset, batch_size=BATCH_SIZE, shuffle=True, num_workers=0,
@@ -60,12 +69,15 @@ class GNN:
             batch_graphs = batch_graphs.to(self.device)
             batch_features = batch_features.to(self.device)
             batch_labels = batch_labels.to(self.device)
-            logits = self.net(batch_graphs, batch_features)
-            loss = self.loss_fcn(logits, batch_labels)
+            if self.trainer is not None and ops.use_stack_path():
+                loss = self.trainer.step(batch_graphs, batch_features, batch_labels)
+            else:
+                logits = self.net(batch_graphs, batch_features)
+                loss = self.loss_fcn(logits, batch_labels)
+                self.optimizer.zero_grad()
+                loss.backward()
+                self.optimizer.step()
             losses.append(loss.detach())          # read back once per epoch, not per step
-            self.optimizer.zero_grad()
-            loss.backward()
-            self.optimizer.step()
         self.lr_decay.step()
         return float(torch.stack(losses).mean().item()) if losses else float("nan")
 

@@ -101,15 +101,38 @@ class BatchedGraph:
             dst = self._dst.to(device, non_blocking=True)
             noff = self._node_off.to(device, non_blocking=True)
             eoff = self._edge_off.to(device, non_blocking=True)
-            if len(self._node_counts) > 1:
-                gsrc, gdst = ops.batch_edges(src, dst, eoff, noff)
-            else:
-                gsrc, gdst = src, dst
-            indptr, indices, eid = ops.csr_build(gdst, gsrc, g.number_of_nodes(), want_eid=True)
-            g.err_flag = torch.zeros(1, dtype=torch.int32, device=device)
-        g._gsrc, g._gdst, g._eid = gsrc, gdst, eid
-        g._csr = (indptr, indices)
-        g._csc = None
+            g._build_on_device(src, dst, noff, eoff)
+        return g
+
+    def _build_on_device(self, src, dst, noff, eoff):
+        """Device side of dgl.batch + the lazy COO->CSR of DGL: global edge ids, then the in-edge CSR (K6)."""
+        device = src.device
+        if len(self._node_counts) > 1:
+            gsrc, gdst = ops.batch_edges(src, dst, eoff, noff)
+        else:
+            gsrc, gdst = src, dst
+        indptr, indices, eid = ops.csr_build(gdst, gsrc, self.number_of_nodes(), want_eid=True)
+        self.err_flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self._gsrc, self._gdst, self._eid = gsrc, gdst, eid
+        self._csr = (indptr, indices)
+        self._csc = None
+
+    @classmethod
+    def from_device_edges(cls, src_local, dst_local, node_off, edge_off, node_counts, edge_counts):
+        """Batched graph whose per-graph LOCAL edge lists (int32) and offsets already live on the device (static
+        input buffers of a CUDA-graphed step, trainer.GraphedStep): only the device build runs, nothing is copied."""
+        g = cls.__new__(cls)
+        g._src = g._dst = None                       # no host copy
+        g._node_counts = [int(n) for n in node_counts]
+        g._edge_counts = [int(e) for e in edge_counts]
+        g._node_off, g._edge_off = node_off, edge_off
+        g.device = src_local.device
+        g.ndata = {}
+        g._csr = g._csc = None
+        g._gsrc = g._gdst = g._eid = None
+        g.err_flag = None
+        with torch.cuda.device(g.device):
+            g._build_on_device(src_local, dst_local, node_off, edge_off)
         return g
 
     def cuda(self):

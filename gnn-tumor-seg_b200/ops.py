@@ -535,11 +535,13 @@ class SageStackFn(torch.autograd.Function):
         L = len(layers)
         N = feats.shape[0]
         dlogits = _row_major_2d(dlogits)
-        # one flat buffer: [dWp | dbp | dWs | dWn | db] per layer, then 2 spare floats (loss sums in DP)
+        # one flat buffer: [dWp | dbp | dWs | dWn | db | db2] per layer, then 2 spare floats (loss sums in DP).
+        # fc_self.bias and fc_neigh.bias get the same values in SEPARATE slices: one tensor returned for two inputs
+        # is cloned by autograd's AccumulateGrad, which would take that .grad out of the flat buffer.
         sizes = []
         for l in range(L):
             Wp, bp, Ws, bs, Wn, bn = flat[6 * l:6 * l + 6]
-            sizes += [Wp.numel(), bp.numel(), Ws.numel(), Wn.numel(), Ws.shape[0]]
+            sizes += [Wp.numel(), bp.numel(), Ws.numel(), Wn.numel(), Ws.shape[0], Ws.shape[0]]
         offs = [0]
         for sz in sizes:
             offs.append(offs[-1] + (sz + 3) // 4 * 4)             # keep every slice 16-byte aligned
@@ -548,10 +550,13 @@ class SageStackFn(torch.autograd.Function):
         outs = []
         for l in range(L):
             Wp, bp, Ws, bs, Wn, bn = flat[6 * l:6 * l + 6]
-            v = [flat_g[offs[5 * l + k]:offs[5 * l + k] + sizes[5 * l + k]] for k in range(5)]
-            gWp, gbp, gWs, gWn, gb = v[0].view_as(Wp), v[1].view_as(bp), v[2].view_as(Ws), v[3].view_as(Wn), v[4]
+            v = [flat_g[offs[6 * l + k]:offs[6 * l + k] + sizes[6 * l + k]] for k in range(6)]
+            gWp, gbp, gWs, gWn, gb, gb2 = v[0].view_as(Wp), v[1].view_as(bp), v[2].view_as(Ws), v[3].view_as(Wn), v[4], v[5]
+            both = bs is not None and bn is not None
             grads[l].dWp, grads[l].dbp, grads[l].dWs, grads[l].dWn, grads[l].db = (ptr(t) for t in (gWp, gbp, gWs, gWn, gb))
-            outs += [gWp, gbp, gWs, gb if bs is not None else None, gWn, gb if bn is not None else None]
+            grads[l].db2 = ptr(gb2) if both else None
+            outs += [gWp, gbp, gWs, gb if bs is not None else None, gWn,
+                     (gb2 if both else gb) if bn is not None else None]
         dfeats = torch.empty_like(feats) if ctx.needs_input_grad[1] else None
         cptr = cidx = None
         if ctx.deterministic:
