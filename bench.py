@@ -32,6 +32,10 @@ LAYER_SIZES = [256] * 7
 IN_FEATS, N_CLASSES = 20, 4
 CLASS_W = [0.1, 1.0, 2.0, 2.0]
 N_DISTINCT_GRAPHS = 8
+WORKLOAD_SAGE = ("GraphSAGE-pool 7x256 training fwd+CE+bwd(+AdamW), batch of 6 synthetic 15k-node supervoxel RAGs per GPU "
+                 "(BASELINE configs[1]; configs[3] for N>1: whole graphs per rank + bucketed NCCL grad all-reduce)")
+WORKLOAD_GAT = ("GAT 4-head x256 (layer_sizes [256]*4, heads [4,4,4,4], residuals [F,F,T,F]) training fwd+CE+bwd(+AdamW), "
+                "batch of 6 synthetic 15k-node supervoxel RAGs per GPU (BASELINE configs[2])")
 # BASELINE configs[2] / SURVEY §8 a5: GAT 4-head x256
 GAT_LAYER_SIZES, GAT_HEADS, GAT_RESIDUALS = [256] * 4, [4, 4, 4, 4], [False, False, True, False]
 
@@ -174,23 +178,32 @@ def model_flops_bytes(n_nodes, n_edges):
 # reference arm: the reference-equivalent CPU path (DGL cannot be installed offline)
 # ---------------------------------------------------------------------------
 def run_reference(args):
+    """The reference-equivalent CPU path on the SAME workload as our arm: one step = forward + weighted CE + backward
+    (+ torch AdamW) over the batch of 6 graphs (block-diagonal union, as dgl.batch makes), all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import graph_ref, sage_ref
-    from gnn_tumor_seg_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    g = synth.make_graph(0)
-    indptr, indices, _ = graph_ref.csr_by_dst_ref(g.src, g.dst, g.n_nodes)
+    graphs = synth_batches(args.batch, 1, 0)[0]
+    off = np.concatenate([[0], np.cumsum([g.n_nodes for g in graphs])])
+    src = np.concatenate([g.src.astype(np.int64) + off[i] for i, g in enumerate(graphs)])
+    dst = np.concatenate([g.dst.astype(np.int64) + off[i] for i, g in enumerate(graphs)])
+    n_nodes, n_edges = int(off[-1]), int(src.size)
+    indptr, indices, _ = graph_ref.csr_by_dst_ref(src, dst, n_nodes)
     torch.manual_seed(0)
     net = sage_ref.GraphSageRef(IN_FEATS, LAYER_SIZES, N_CLASSES)
-    x, y, w = torch.as_tensor(g.features), torch.as_tensor(g.labels), torch.tensor(CLASS_W)
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-4)
+    x = torch.as_tensor(np.concatenate([g.features for g in graphs]))
+    y = torch.as_tensor(np.concatenate([g.labels for g in graphs]))
+    w = torch.tensor(CLASS_W)
 
     def step():
-        net.zero_grad()
         loss = torch.nn.functional.cross_entropy(net((indptr, indices), x), y, weight=w)
+        opt.zero_grad()
         loss.backward()
+        opt.step()
         return float(loss)
 
     for _ in range(args.warmup):
@@ -199,15 +212,17 @@ def run_reference(args):
     for _ in range(args.steps):
         step()
     dt = (time.perf_counter() - t0) / args.steps
-    gps = 1.0 / dt
-    sample = "1 of the 6 graphs of a batch per step (15000 nodes, %d edges), fwd+CE+bwd" % g.n_edges
+    gps = args.batch / dt
+    sample = "%d steps x (batch of %d graphs: %d nodes, %d edges) fwd+CE+bwd+AdamW" % (args.steps, args.batch, n_nodes, n_edges)
     line = {
         "impl": "reference", "metric": "graphs_per_s", "value": gps, "unit": "graphs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "edges_per_s": gps * g.n_edges,
-        "config": {"workload": "GraphSAGE-pool 7x256 training fwd+bwd, synthetic 15k-node supervoxel RAGs (BASELINE configs[1])",
-                   "note": "reference-equivalent CPU path: pure-PyTorch restatement of DGL SAGEConv('pool'); DGL is not installable offline",
+        "edges_per_s": n_edges / dt,
+        "config": {"workload": WORKLOAD_SAGE, "layer_sizes": LAYER_SIZES, "graphs_per_gpu": args.batch,
+                   "nodes_per_step_per_gpu": n_nodes, "edges_per_step_per_gpu": n_edges,
+                   "note": "reference-equivalent CPU path: pure-PyTorch restatement of DGL SAGEConv('pool') (oracle/sage_ref.py); "
+                           "DGL is not installable offline",
                    "threads": torch.get_num_threads()},
         "cpu_baseline": {"value": gps, "unit": "graphs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": gps, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -311,11 +326,26 @@ def run_ours(args):
     else:
         net = networks.GraphSage(IN_FEATS, LAYER_SIZES, N_CLASSES, "pool", 0).to(dev)
     class_w = torch.tensor(CLASS_W, device=dev)
-    trainer = dp.DataParallelTrainer(net, class_w)
+    # one step = forward + weighted CE + backward (+ bucketed gradient all-reduce) + AdamW, the reference's loop body
+    # (model/gnn_model.py:41-47) with its hyper-parameters (lr 1e-4, weight decay 1e-4)
+    from gnn_tumor_seg_b200.trainer import FusedAdamW, GraphedStep, SageTrainer
+    if args.model == "sage":
+        trainer = SageTrainer(net, class_w, lr=1e-4, weight_decay=1e-4)
+
+        def train_step(bg, f, l):
+            return trainer.step(bg, f, l)
+    else:
+        trainer = dp.DataParallelTrainer(net, class_w)
+        gat_opt = FusedAdamW(net.parameters(), lr=1e-4, weight_decay=1e-4)
+
+        def train_step(bg, f, l):
+            loss = trainer.forward_backward(bg, f, l)
+            gat_opt.step()
+            return loss
 
     def step(i):
         bg, f, l = resident[i % len(resident)]
-        return trainer.forward_backward(bg, f, l)
+        return train_step(bg, f, l)
 
     def barrier():
         if world > 1:
@@ -340,32 +370,65 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1) / args.steps
     loss_val = float(loss)
+    ms_eager = ms
 
     # ---- end to end from pinned host buffers through the public API ----
-    # every step: H2D of the step's edge lists / features / labels from pinned memory + device CSR build, forward, loss,
-    # backward, D2H read of the step's loss.  Default ("sync"): the reference's loss.item() per step
-    # (model/gnn_model.py:43) with in-stream .to(device): 5.4-5.5 ms against ~5.0 device-resident - after each sync the
-    # host has to catch up with the device.  GTS_BENCH_E2E=async: every step's loss copied to pinned host memory without
-    # stalling the host, inputs staged by data_loader.DevicePrefetcher, one synchronisation at the end: 5.34 ms in two
-    # runs and 11.5 ms in a third (side-stream staging is not yet robust: see DESIGN.md), hence not the default.
-    from gnn_tumor_seg_b200.data_loader import DevicePrefetcher
-    e2e_mode = os.environ.get("GTS_BENCH_E2E", "sync")
-    loss_host = torch.zeros(max(args.steps, 8), dtype=torch.float32).pin_memory()
+    # every step: H2D of the step's edge lists / features / labels from pinned memory, the device CSR build, forward,
+    # loss, backward, AdamW, and a D2H read of the step's loss — all inside the timed region.
+    #  "graph" (default, single GPU, SAGE): trainer.GraphedStep — the whole step incl. the CSR build replayed from a CUDA
+    #      graph (one per batch signature), the H2D copies of step i+1 staged on a copy stream while step i computes,
+    #      the host reads step i's loss (pinned, D2H'd behind the step) after it has enqueued step i+1;
+    #  "eager" (N > 1, GAT): the same pipeline without the CUDA graph (in-stream .to(device));
+    #  "sync": the reference's blocking loss.item() per step (model/gnn_model.py:43) — GTS_BENCH_E2E=sync.
+    e2e_mode = os.environ.get("GTS_BENCH_E2E", "graph" if (world == 1 and args.model == "sage") else "eager")
+    K = 8
+    loss_host = torch.zeros(K, dtype=torch.float32).pin_memory()
+    loss_ev = [torch.cuda.Event() for _ in range(K)]
+    gsteps, copy_stream = None, None
+    if e2e_mode == "graph":
+        gsteps = [GraphedStep(trainer, *pinned[k]) for k in range(len(pinned))]
+        copy_stream = torch.cuda.Stream(device=dev)
 
     def e2e_steps(n):
-        src = (pinned[i % len(pinned)] for i in range(n))
         ls = None
         if e2e_mode == "sync":
-            for bg, f, l in src:
-                ls = float(trainer.forward_backward(bg.to(dev), f.to(dev, non_blocking=True), l.to(dev, non_blocking=True)))
-        else:
-            for i, (dg, f, l) in enumerate(DevicePrefetcher(src, dev)):
-                t = trainer.forward_backward(dg, f, l)
-                loss_host[i % loss_host.numel()].copy_(t.detach(), non_blocking=True)      # D2H read of the step's loss
-            torch.cuda.current_stream().synchronize()
-            ls = float(loss_host[(n - 1) % loss_host.numel()])
-        return ls
+            for i in range(n):
+                bg, f, l = pinned[i % len(pinned)]
+                ls = float(train_step(bg.to(dev), f.to(dev, non_blocking=True), l.to(dev, non_blocking=True)))
+            return ls
+        for i in range(n):
+            bg, f, l = pinned[i % len(pinned)]
+            if e2e_mode == "graph":
+                gs = gsteps[i % len(gsteps)]
+                gs.load_async(bg, f, l, copy_stream)           # H2D on the copy stream, overlaps the previous step
+                t = gs.replay()
+            else:
+                t = train_step(bg.to(dev), f.to(dev, non_blocking=True), l.to(dev, non_blocking=True))
+            loss_host[i % K].copy_(t.detach(), non_blocking=True)      # D2H read of THIS step's loss
+            loss_ev[i % K].record()
+            if i > 0:                                           # the host consumes step i-1's loss while step i runs
+                loss_ev[(i - 1) % K].synchronize()
+                ls = float(loss_host[(i - 1) % K])
+        loss_ev[(n - 1) % K].synchronize()
+        return float(loss_host[(n - 1) % K])
 
+    if gsteps is not None:
+        # device-resident number of the product's fixed-shape path: the same captured steps replayed on inputs that
+        # already sit in their static device buffers (no H2D); the eager figure above stays in the line beside it
+        for i in range(args.warmup):
+            gsteps[i % len(gsteps)].replay()
+        barrier()
+        sampler2 = ClockSampler(local_rank)
+        sampler2.start()
+        g0_, g1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0_.record()
+        for i in range(args.steps):
+            loss = gsteps[i % len(gsteps)].replay()
+        g1_.record()
+        barrier()
+        clocks = sampler2.stop()
+        ms = g0_.elapsed_time(g1_) / args.steps
+        loss_val = float(loss)
     e2e_steps(max(3, args.warmup // 2))
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -391,7 +454,19 @@ def run_ours(args):
     # ---- per-kernel breakdown and live roofline of the dominant + aggregation kernels ----
     # rank 0 only from here on: no collectives (the other ranks are already waiting at the final barrier)
     trainer.world_size = 1
-    breakdown = kernel_breakdown(lambda: step(0), ops)
+
+    def autograd_step():           # the same kernels through the per-op wrappers (attributable launches)
+        bg, f, l = resident[0]
+        for p_ in net.parameters():
+            p_.grad = None
+        ops.weighted_cross_entropy(net(bg, f), l, class_w).backward()
+
+    breakdown = kernel_breakdown(autograd_step, ops)
+    opt = trainer.optimizer if args.model == "sage" else gat_opt
+    for p_ in net.parameters():
+        if p_.grad is None:
+            p_.grad = torch.zeros_like(p_)
+    breakdown["adamw_step"] = {"ms": time_kernel(lambda i: opt.step(), 20), "calls": 1}
     D = 256
     Ps = [torch.relu(torch.randn(n_nodes, D, device=dev)) for _ in range(3)]      # 3 x 92 MB > L2
     indptr, indices = resident[0][0].csr
@@ -401,7 +476,7 @@ def run_ours(args):
     args_ = [ops.segmax_fwd(Ps[i], indptr, indices)[1] for i in range(3)]
     dNs = [torch.randn(n_nodes, D, device=dev) for _ in range(3)]
     ms_segb = time_kernel(lambda i: ops.segmax_bwd(dNs[i % 3], args_[i % 3], n_nodes), 30)
-    segb_bytes = 4 * (4 * n_nodes * D)            # dNeigh + argmax reads, dP zero-fill + dP atomics
+    segb_bytes = 4 * (3 * n_nodes * D)            # dNeigh + arg-max reads, dP written once (a zero-fill pass is not compulsory traffic)
     W = torch.randn(D, D, device=dev)
     bias = torch.randn(D, device=dev)
     ms_gemm = time_kernel(lambda i: ops.gemm_nt(Ps[i % 3], W, Ps[(i + 1) % 3], W, bias=bias, act=1), 10)
@@ -446,31 +521,39 @@ def run_ours(args):
                     "unit": "GB/s", "frac": k["frac"], "traffic": k.get("traffic"),
                     "note": "algorithmic bytes 4*(3*N*D + N+1 + E) / CUDA-event time; peak %s" % peaks["src"]}
 
-    # ---- CPU baseline (oracle, bounded sample) ----
+    # ---- CPU baseline (oracle, bounded sample of the SAME workload: the batch of 6 graphs per step) ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import graph_ref, sage_ref
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        g = host_batches[0][0]
-        ip, ix, _ = graph_ref.csr_by_dst_ref(g.src, g.dst, g.n_nodes)
+        gs_ = host_batches[0]
+        off = np.concatenate([[0], np.cumsum([g.n_nodes for g in gs_])])
+        src_ = np.concatenate([g.src.astype(np.int64) + off[i] for i, g in enumerate(gs_)])
+        dst_ = np.concatenate([g.dst.astype(np.int64) + off[i] for i, g in enumerate(gs_)])
+        ip, ix, _ = graph_ref.csr_by_dst_ref(src_, dst_, int(off[-1]))
         torch.manual_seed(0)
         ref = sage_ref.GraphSageRef(IN_FEATS, LAYER_SIZES, N_CLASSES)
-        x, y, w = torch.as_tensor(g.features), torch.as_tensor(g.labels), torch.tensor(CLASS_W)
+        ropt = torch.optim.AdamW(ref.parameters(), lr=1e-4, weight_decay=1e-4)
+        x = torch.as_tensor(np.concatenate([g.features for g in gs_]))
+        y = torch.as_tensor(np.concatenate([g.labels for g in gs_]))
+        w = torch.tensor(CLASS_W)
 
         def cstep():
-            ref.zero_grad()
-            torch.nn.functional.cross_entropy(ref((ip, ix), x), y, weight=w).backward()
+            loss_c = torch.nn.functional.cross_entropy(ref((ip, ix), x), y, weight=w)
+            ropt.zero_grad()
+            loss_c.backward()
+            ropt.step()
         cstep()
         t0 = time.perf_counter()
         n_c = 0
-        while n_c < 3 or (time.perf_counter() - t0 < 12 and n_c < 10):
+        while n_c < 2 or (time.perf_counter() - t0 < 15 and n_c < 6):
             cstep()
             n_c += 1
         dt = (time.perf_counter() - t0) / n_c
-        cpu = {"value": 1.0 / dt, "unit": "graphs/s", "cores": cores, "kind": "port",
-               "sample": "%d x (1 graph of the batch: 15000 nodes, %d edges) fwd+CE+bwd, PyTorch CPU oracle "
-                         "(DGL not installable offline)" % (n_c, g.n_edges)}
+        cpu = {"value": args.batch / dt, "unit": "graphs/s", "cores": cores, "kind": "port",
+               "sample": "%d steps x (batch of %d graphs: %d nodes, %d edges) fwd+CE+bwd+AdamW, PyTorch CPU oracle "
+                         "(DGL not installable offline)" % (n_c, args.batch, int(off[-1]), int(src_.size))}
 
     total_graphs = args.batch * world
     line = {
@@ -478,11 +561,7 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3"}[args.mode], "data": "synthetic",
         "edges_per_s": n_edges * world / (ms * 1e-3),
-        "config": {"workload": ("GraphSAGE-pool 7x256 training fwd+CE+bwd, batch of 6 synthetic 15k-node supervoxel RAGs per GPU "
-                                "(BASELINE configs[1]; configs[3] for N>1: whole graphs per rank + one NCCL grad all-reduce)")
-                               if args.model == "sage" else
-                               ("GAT 4-head x256 (layer_sizes [256]*4, heads [4,4,4,4], residuals [F,F,T,F]) training fwd+CE+bwd, "
-                                "batch of 6 synthetic 15k-node supervoxel RAGs per GPU (BASELINE configs[2])"),
+        "config": {"workload": WORKLOAD_SAGE if args.model == "sage" else WORKLOAD_GAT,
                    "layer_sizes": LAYER_SIZES if args.model == "sage" else GAT_LAYER_SIZES, "graphs_per_gpu": args.batch, "nodes_per_step_per_gpu": n_nodes,
                    "edges_per_step_per_gpu": n_edges, "gemm_mode": args.mode,
                    "l2_policy": "inputs larger than L2: %d rotating device-resident batches, >2 GB of activations per step" % args.rotate,
@@ -490,10 +569,17 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": total_graphs / (ms_e2e * 1e-3), "unit": "graphs/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h, "loss": loss_e2e,
-                "loss_read": ("one blocking loss.item() per step" if e2e_mode == "sync" else
-                              "every step's loss copied D2H into pinned memory (non-blocking), one sync at the end of the timed "
-                              "region; inputs of step i+1 staged on a side stream (GTS_BENCH_E2E=sync for loss.item() per step)")},
+                "mode": e2e_mode,
+                "loss_read": {"graph": "every step's loss D2H-copied into pinned memory behind the step and read by the host one "
+                                       "step later (while the next step runs); H2D of step i+1 on a copy stream; step replayed "
+                                       "from a CUDA graph (trainer.GraphedStep)",
+                              "eager": "every step's loss D2H-copied into pinned memory and read by the host one step later; "
+                                       "in-stream .to(device)",
+                              "sync": "one blocking loss.item() per step"}[e2e_mode]},
         "gpu_launches": int(launches),
+        "eager_ms_per_step": ms_eager,
+        "value_path": ("CUDA-graph replay of the step (trainer.GraphedStep, incl. the device CSR build), inputs resident in "
+                       "their static device buffers" if gsteps is not None else "eager trainer step, inputs and CSR resident"),
         "roofline": roofline,
         "kernels": kern,
         "step_breakdown": share,
@@ -501,10 +587,10 @@ def run_ours(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
+    return line
 
 
 
@@ -650,10 +736,10 @@ def run_infer(args):
                          "note": "reprojection kernel alone (24 MB per launch: launch- and latency-bound); the job is dominated "
                                  "by the eval forward"},
         }
-        print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
+    return line if rank == 0 else None
 
 
 def main():
@@ -667,19 +753,44 @@ def main():
     ap.add_argument("--batch", type=int, default=6)
     ap.add_argument("--rotate", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the GAT / bulk-inference riders of the default line")
     ap.add_argument("--workload", default="train", choices=["train", "infer"],
                     help="train = BASELINE configs[1]/[3] (the headline); infer = configs[4] bulk inference + reprojection")
     ap.add_argument("--infer-graphs", type=int, default=1251)
     ap.add_argument("--infer-batch", type=int, default=6, help="graphs per eval forward (1 = the reference's per-graph loop)")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "infer":
+        return
+    if args.workload == "infer":
         args.steps = min(args.steps, 3)
-        run_infer(args)
+        line = run_infer(args)
     else:
         args.warmup = max(args.warmup, 3)
-        run_ours(args)
+        line = run_ours(args)
+        # The other named single-GPU configurations ride along as extra keys of the default line (N = 1, SAGE), each
+        # with its own roofline: BASELINE configs[2] (GAT 4-head x256) and configs[4] (bulk inference + reprojection).
+        if line is not None and world == 1 and args.model == "sage" and not args.no_extras:
+            import copy
+            keep = ("value", "unit", "ms_per_step", "edges_per_s", "dtype", "config", "e2e", "gpu_launches", "roofline",
+                    "kernels", "step_breakdown", "steps", "warmup", "scaling")
+            try:
+                a2 = copy.copy(args)
+                a2.model, a2.steps, a2.warmup, a2.no_cpu_baseline = "gat", min(args.steps, 8), 3, True
+                g = run_ours(a2)
+                line["config2_gat"] = {k: g[k] for k in keep if k in g}
+            except Exception as e:          # an extra must not cost the headline line
+                line["config2_gat"] = {"error": repr(e)[:300]}
+            try:
+                a4 = copy.copy(args)
+                a4.steps = 2
+                g = run_infer(a4)
+                line["config4_bulk_inference"] = {k: g[k] for k in keep if k in g}
+            except Exception as e:
+                line["config4_bulk_inference"] = {"error": repr(e)[:300]}
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

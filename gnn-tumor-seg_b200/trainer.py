@@ -351,6 +351,31 @@ class GraphedStep:
         self.feats.copy_(feats, non_blocking=True)
         self.labels.copy_(labels, non_blocking=True)
 
+    def load_async(self, host_graph, feats, labels, stream):
+        """Stage the next batch with this signature on ``stream`` (a copy stream) while other work runs on the compute
+        stream: the copies wait for the previous replay of THIS object (the last reader of its static buffers)."""
+        if self.signature_of(host_graph, feats) != self.signature:
+            raise GtsError("GraphedStep: batch signature differs from the captured one")
+        if getattr(self, "_done", None) is not None:
+            stream.wait_event(self._done)
+        with torch.cuda.stream(stream):
+            self._load(host_graph, feats, labels)
+        self._loaded = torch.cuda.Event()
+        self._loaded.record(stream)
+
+    def replay(self):
+        """Run the captured step on the current stream once the staged inputs have landed; returns the loss (0-d device
+        tensor, overwritten by the next replay of this object)."""
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_loaded", None) is not None:
+            cur.wait_event(self._loaded)
+            self._loaded = None
+        self.trainer.optimizer._sync_lr()
+        self.graph.replay()
+        self._done = torch.cuda.Event()
+        self._done.record(cur)
+        return self.loss
+
     def __call__(self, host_graph, feats, labels):
         """One step on a batch with this signature; returns the loss (0-d device tensor, overwritten by the next
         replay)."""
