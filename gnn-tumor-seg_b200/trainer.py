@@ -308,11 +308,16 @@ class GraphedStep:
     static device input buffers <- (async H2D copies, outside the graph) <- pinned host batch; graph = batched edge
     list + CSR build (K6) + forward + CE + backward + AdamW + loss.  Replay costs one launch on the host side."""
 
-    def __init__(self, trainer: SageTrainer, host_graph, feats, labels):
+    def __init__(self, trainer: SageTrainer, host_graph, feats, labels, capture: bool = True):
+        """capture=False keeps the static input buffers and the copy-stream staging but runs the step eagerly on
+        replay (data-parallel steps: the NCCL collectives stay outside CUDA graphs)."""
         from .graph import BatchedGraph
-        if trainer.world_size != 1:
-            raise GtsError("GraphedStep: single-device steps only (collectives stay on the eager path)")
+        if trainer.world_size != 1 and capture:
+            # tried on 2 x B200 (torch 2.11 / NCCL 2.28): capturing the async bucketed all-reduces hung the ranks
+            raise GtsError("GraphedStep: single-device steps only (collectives stay on the eager path: capture=False)")
         self.trainer = trainer
+        self._BatchedGraph = BatchedGraph
+        self.graph = None
         dev = trainer.arena.params.device
         self.signature = self.signature_of(host_graph, feats)
         self.src = torch.empty_like(host_graph._src, device=dev)
@@ -324,6 +329,8 @@ class GraphedStep:
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
         self._node_counts, self._edge_counts = list(host_graph._node_counts), list(host_graph._edge_counts)
         self._load(host_graph, feats, labels)
+        if not capture:
+            return
         # warm-up on a side stream (lazy initialisation: function attributes, tensor-map entry point), then capture
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(dev))
@@ -371,7 +378,10 @@ class GraphedStep:
             cur.wait_event(self._loaded)
             self._loaded = None
         self.trainer.optimizer._sync_lr()
-        self.graph.replay()
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._body(self._BatchedGraph)
         self._done = torch.cuda.Event()
         self._done.record(cur)
         return self.loss
@@ -382,6 +392,4 @@ class GraphedStep:
         if self.signature_of(host_graph, feats) != self.signature:
             raise GtsError("GraphedStep: batch signature differs from the captured one")
         self._load(host_graph, feats, labels)
-        self.trainer.optimizer._sync_lr()
-        self.graph.replay()
-        return self.loss
+        return self.replay()
