@@ -147,8 +147,8 @@ gat_fwd_kernel(const float* __restrict__ Z, int64_t ldz, const float* __restrict
       float s = -INFINITY;
       if (on) s = lrelu(el[(int64_t)indices[base + lane] * H + h] + erv, slope);
       const float m_new = fmaxf(m, warp_max(s));
-      const float part = warp_sum(on ? __expf(s - m_new) : 0.f);
-      l = l * __expf(m - m_new) + part;
+      const float part = warp_sum(on ? expf(s - m_new) : 0.f);
+      l = l * expf(m - m_new) + part;
       m = m_new;
     }
     // pass B: weighted gather of neighbour rows
@@ -161,7 +161,7 @@ gat_fwd_kernel(const float* __restrict__ Z, int64_t ldz, const float* __restrict
       float a_l = 0.f;
       if (on) {
         u_l = indices[base + lane];
-        a_l = __expf(lrelu(el[(int64_t)u_l * H + h] + erv, slope) - m) * inv_l;
+        a_l = expf(lrelu(el[(int64_t)u_l * H + h] + erv, slope) - m) * inv_l;
       }
       const int cnt = min(32, end - base);
       for (int j = 0; j < cnt; ++j) {
@@ -258,7 +258,7 @@ gat_bwd_dst_kernel(const float* __restrict__ Z, int64_t ldz, const float* __rest
         if (lane == j) my_da = d;
       }
       if (on) {
-        const float alpha = __expf(lrelu(el[(int64_t)u_l * H + h] + erv, slope) - m) * inv_l;
+        const float alpha = expf(lrelu(el[(int64_t)u_l * H + h] + erv, slope) - m) * inv_l;
         delta_part = fmaf(alpha, my_da, delta_part);
         dt_edge[(int64_t)(base + lane) * H + h] = my_da;    // parked; finalised in sweep 2 by the same lane
       }
@@ -270,7 +270,7 @@ gat_bwd_dst_kernel(const float* __restrict__ Z, int64_t ldz, const float* __rest
       if (base + lane < end) {
         const int32_t u = indices[base + lane];
         const float t = el[(int64_t)u * H + h] + erv;
-        const float alpha = __expf(lrelu(t, slope) - m) * inv_l;
+        const float alpha = expf(lrelu(t, slope) - m) * inv_l;
         const int64_t idx = (int64_t)(base + lane) * H + h;
         const float ds = alpha * (dt_edge[idx] - delta);
         const float dt = t > 0.f ? ds : ds * slope;
@@ -328,7 +328,7 @@ gat_bwd_src_kernel(const float* __restrict__ el, const float* __restrict__ er, c
       if (on) {
         v_l = cidx[base + lane];
         const int64_t vh = (int64_t)v_l * H + h;
-        a_l = __expf(lrelu(elu_ + er[vh], slope) - rowmax[vh]) / rowsum[vh];
+        a_l = expf(lrelu(elu_ + er[vh], slope) - rowmax[vh]) / rowsum[vh];
         del_part += dt_edge[(int64_t)csc2csr[base + lane] * H + h];
       }
       const int cnt = min(32, end - base);

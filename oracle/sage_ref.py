@@ -128,3 +128,63 @@ def sage_pool_dense_ref(h, adj, Wp, bp, Ws, Wn, b, relu_out):
     neigh = torch.where(adj.any(dim=1, keepdim=True), neigh, torch.zeros_like(neigh))
     out = h @ Ws.T + neigh @ Wn.T + b
     return torch.relu(out) if relu_out else out
+
+
+# ---------------------------------------------------------------------------
+# Tie-aware comparison (tests/test_gpu_full_config.py).  The stack is piecewise linear: every arg-max of the
+# neighbour pooling and every ReLU is a DECISION; two fp32 evaluations with different summation orders agree on all
+# but the handful of decisions whose inputs sit within rounding of a tie, and each flipped decision re-routes a whole
+# gradient contribution.  So the oracle can (a) report its own decisions and (b) evaluate forward + backward with the
+# decisions of another run imposed: same routing, its own arithmetic — then gradients are comparable element-wise.
+# ---------------------------------------------------------------------------
+def graphsage_decisions(ref: "GraphSageRef", csr, features):
+    """Free forward.  Returns (logits, decisions); decisions[l] = {'arg': int64 [N,Din] first-maximum arg-max,
+    'neigh_pos': bool [N,Din] (pooled feature at the arg-max > 0, i.e. fc_pool's ReLU at the selected entry),
+    'out_pos': bool [N,Dout] (output ReLU, None for the last layer)}."""
+    indptr, indices = csr
+    h = features
+    decisions = []
+    with torch.no_grad():
+        for layer in ref.layers:
+            P = F.relu(layer.fc_pool(h))
+            neigh, arg = segment_max_first_ref(P, indptr, indices)
+            rst = layer.fc_self(h) + layer.fc_neigh(neigh)
+            d = {"arg": arg, "neigh_pos": neigh > 0, "out_pos": None}
+            if layer.activation is not None:
+                d["out_pos"] = rst > 0
+                rst = layer.activation(rst)
+            decisions.append(d)
+            h = rst
+    return h, decisions
+
+
+def graphsage_forward_forced(ref: "GraphSageRef", features, decisions):
+    """Differentiable forward with the arg-max routing and the ReLU masks IMPOSED (decisions of another evaluation):
+    neigh[v,k] = pre_pool[arg[v,k],k] * neigh_pos[v,k];  out = (fc_self(h) + fc_neigh(neigh)) * out_pos."""
+    h = features
+    for layer, d in zip(ref.layers, decisions):
+        pre = layer.fc_pool(h)
+        arg = d["arg"]
+        gathered = torch.gather(pre, 0, arg.clamp(min=0))
+        neigh = gathered * (d["neigh_pos"] & (arg >= 0)).to(pre.dtype)
+        rst = layer.fc_self(h) + layer.fc_neigh(neigh)
+        if d["out_pos"] is not None:
+            rst = rst * d["out_pos"].to(rst.dtype)
+        h = rst
+    return h
+
+
+def count_decision_flips(a, b):
+    """Number of differing decisions between two decision lists: (arg-max flips, pool-ReLU flips, output-ReLU flips, total
+    decisions of each kind)."""
+    n_arg = n_pool = n_out = 0
+    t_arg = t_out = 0
+    for x, y in zip(a, b):
+        n_arg += int((x["arg"] != y["arg"]).sum())
+        n_pool += int((x["neigh_pos"] != y["neigh_pos"]).sum())
+        t_arg += x["arg"].numel()
+        if x["out_pos"] is not None:
+            n_out += int((x["out_pos"] != y["out_pos"]).sum())
+            t_out += x["out_pos"].numel()
+    return {"argmax_flips": n_arg, "pool_relu_flips": n_pool, "out_relu_flips": n_out,
+            "argmax_decisions": t_arg, "out_relu_decisions": t_out}
