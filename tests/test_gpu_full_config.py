@@ -14,7 +14,7 @@ import torch.nn.functional as F
 
 from gnn_tumor_seg_b200 import graph as G, networks, ops, synth
 from gnn_tumor_seg_b200.trainer import SageTrainer
-from oracle import gat_ref, graph_ref, sage_ref
+from oracle import compare, gat_ref, graph_ref, sage_ref
 
 pytestmark = pytest.mark.gpu
 W = [0.1, 1.0, 2.0, 2.0]
@@ -31,34 +31,7 @@ def _rel_max(a, b):
 
 
 def _gpu_run_with_decisions(net, dg, x, y, w):
-    """Per-layer autograd path with the decisions recorded: arg-max + (neigh > 0) from segmax_fwd, (out > 0) from the
-    hidden layers' outputs."""
-    rec = {"seg": [], "out": []}
-    orig = ops.segmax_fwd
-
-    def seg(P, indptr, indices, want_argmax=True):
-        neigh, arg = orig(P, indptr, indices, want_argmax=want_argmax)
-        rec["seg"].append((arg.cpu().long(), (neigh > 0).cpu()))
-        return neigh, arg
-
-    hooks = [l.register_forward_hook(lambda m, i, o: rec["out"].append((o > 0).cpu())) for l in net.layers]
-    ops.set_stack_path(False)
-    ops.segmax_fwd = seg
-    try:
-        for p in net.parameters():
-            p.grad = None
-        logits = net(dg, x)
-        loss = ops.weighted_cross_entropy(logits, y, w)
-        loss.backward()
-    finally:
-        ops.segmax_fwd = orig
-        ops.set_stack_path(True)
-        for h in hooks:
-            h.remove()
-    L = len(net.layers)
-    decisions = [{"arg": rec["seg"][l][0], "neigh_pos": rec["seg"][l][1],
-                  "out_pos": rec["out"][l] if l + 1 < L else None} for l in range(L)]
-    return logits.detach().cpu(), float(loss.detach()), {n: p.grad.detach().cpu().clone() for n, p in net.named_parameters()}, decisions
+    return compare.gpu_sage_step_with_decisions(net, ops, dg, x, y, w)
 
 
 @pytest.mark.parametrize("mode", ["tf32x3"])

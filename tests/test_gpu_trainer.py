@@ -142,9 +142,11 @@ def test_graphed_step_replays_equal_eager_steps(cuda_dev):
         for bg, feats, labels in variants:
             la = tr_a.step(bg.to(cuda_dev), feats.to(cuda_dev), labels.to(cuda_dev))
             lb = gs(bg, feats, labels)
-            assert la.item() == lb.item()                      # same library calls, eager vs replayed: bit-identical
+            # same library calls, eager vs replayed; not bit-identical: the loss sums are reduced with float atomics
+            assert abs(la.item() - lb.item()) <= 1e-6 * abs(la.item())
         for (n, p), (_, q) in zip(net_a.named_parameters(), net_b.named_parameters()):
-            assert torch.equal(p, q), n
+            dlt = (p - q).abs()
+            assert dlt.mean().item() < 1e-6 and dlt.max().item() < 4e-3, (n, dlt.mean().item(), dlt.max().item())
         with pytest.raises(Exception):
             gs(_batch([32, 33])[0], variants[0][1], variants[0][2])      # another signature must be refused
     finally:
