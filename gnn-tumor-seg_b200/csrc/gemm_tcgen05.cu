@@ -964,6 +964,41 @@ __device__ __forceinline__ void mma_x3bf_block_ts2(uint32_t d_tmem, uint32_t a_h
       ::"r"(d_tmem), "r"(a_hi), "r"(b_lo32), "r"(l_lo32), "r"(desc_hi32), "r"(idesc), "r"(idesc_bf), "r"(first) : "memory");
 }
 
+// TN (weight-gradient) form of the bf16-cross-term k-block.  hi*hi: four TF32 MMAs on the MN-major fp32 B tile as in
+// mma_x3_block_ts2 (k-step = k16 descriptor units); the cross terms: 2 + 2 bf16 MMAs (K = 16) whose B operand is an
+// MN-major bf16 tile in the standard 128-byte swizzle (one 128-byte row of this CTA's 64 n-values per k, 8 k-rows per
+// 1024-byte swizzle atom, SBO = 1024): h_lo32 / l_lo32 = low descriptor words of the bf16(B) / bf16(B_lo) tiles at
+// k-step 0, the second K = 16 step is two atoms (2048 B = 128 units) further.  A parts in TMEM as in the NT form.
+__device__ __forceinline__ void mma_x3bf_block_ts2_tn(uint32_t d_tmem, uint32_t a_hi, uint32_t b_lo32, uint32_t k16,
+                                                      uint32_t desc_hi32, uint32_t h_lo32, uint32_t l_lo32,
+                                                      uint32_t desc_bf_hi32, uint32_t idesc, uint32_t idesc_bf, uint32_t first) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pf, pt, pe;\n\t"
+      ".reg .b32 x1, x2, x3, y1, z1, ah1, ah2, ah3, al0, al1, ab0, ab1;\n\t"
+      ".reg .b64 b0, b1, b2, b3, h0, h1, l0, l1;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pf, %10, 0;\n\t"
+      "setp.eq.b32 pt, %10, %10;\n\t"
+      "add.u32 x1, %2, %3;\n\t add.u32 x2, x1, %3;\n\t add.u32 x3, x2, %3;\n\t"
+      "add.u32 y1, %5, 128;\n\t add.u32 z1, %6, 128;\n\t"
+      "mov.b64 b0, {%2, %4};\n\t mov.b64 b1, {x1, %4};\n\t mov.b64 b2, {x2, %4};\n\t mov.b64 b3, {x3, %4};\n\t"
+      "mov.b64 h0, {%5, %7};\n\t mov.b64 h1, {y1, %7};\n\t mov.b64 l0, {%6, %7};\n\t mov.b64 l1, {z1, %7};\n\t"
+      "add.u32 ah1, %1, 8;\n\t add.u32 ah2, %1, 16;\n\t add.u32 ah3, %1, 24;\n\t"
+      "add.u32 al0, %1, 32;\n\t add.u32 al1, %1, 40;\n\t add.u32 ab0, %1, 48;\n\t add.u32 ab1, %1, 56;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], b0, %8, pf;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [ah1], b1, %8, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [ah2], b2, %8, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [ah3], b3, %8, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], [al0], h0, %9, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], [al1], h1, %9, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], [ab0], l0, %9, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], [ab1], l1, %9, pt;\n\t"
+      "}"
+      ::"r"(d_tmem), "r"(a_hi), "r"(b_lo32), "r"(k16), "r"(desc_hi32), "r"(h_lo32), "r"(l_lo32), "r"(desc_bf_hi32),
+        "r"(idesc), "r"(idesc_bf), "r"(first) : "memory");
+}
+
 // BF == 2: as above, but the hi*hi TF32 product reads A straight from the TMA-landed shared-memory tile (SS form:
 // the raw fp32 tile IS the hi operand, the MMA truncates it), so a TMEM slot holds only the two bf16 parts
 // ([0,16) bf16x2(A_lo) | [16,32) bf16x2(A)) and the ring is 8 slots deep instead of 4.
@@ -1003,7 +1038,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Ts2Cfg::THREADS, 1)
 gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, const Params p) {
   static_assert(!DUAL || TN, "the two-B form exists for the weight-gradient GEMM only");
-  static_assert(!BF || !TN, "bf16 cross terms: NT form only");
+  static_assert(!(TN && BF == 2), "TN form: bf16 cross terms with the A operand in tensor memory (BF == 1) only");
   using L = Ts2CfgT<DUAL, BF>;
   constexpr int NB = L::NB;
   constexpr int STAGES = L::STAGES;
@@ -1107,7 +1142,9 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     if (rank == 0) {
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);          // warp-uniform copy
       const uint32_t idesc = make_idesc_ts(2 * BM, p.BN, TN);
-      const uint32_t idesc_bf = make_idesc_ts_bf16(2 * BM, p.BN);
+      const uint32_t idesc_bf = make_idesc_ts_bf16(2 * BM, p.BN) | (TN ? (1u << 16) : 0u);      // TN: B MN-major
+      // bf16 B tiles of the TN form: MN-major, standard 128-byte swizzle, SBO = 1024 B between 8-k-row atoms
+      const uint32_t desc_bf_hi = (uint32_t)(make_smem_desc(0, 2048, 1024, kLayoutSw128) >> 32);
       // descriptor of a B tile at shared-memory address 0; the address field (bits 0..13, 16-byte units) is added per use
       const uint64_t desc0 = make_smem_desc(0, TN ? 4096 : 16, TN ? 512 : 1024, TN ? kLayoutSw128Base32 : kLayoutSw128);
       const uint32_t desc0_lo = (uint32_t)desc0, desc0_hi = (uint32_t)(desc0 >> 32);
@@ -1138,6 +1175,10 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
               if (BF == 2)     // A tile of this stage: same descriptor fields as a K-major B tile (128 rows instead of 64)
                 mma_x3bf2_block_ts2(d_tmem, a_hi, bb - (A_STAGE_BYTES >> 4), bb, bb + (L::B_HALF_BYTES >> 4), desc0_hi,
                                     make_idesc(2 * BM, p.BN, false), idesc_bf, (kb > kb_beg || j > 0) ? 1u : 0u);
+              else if (BF == 1 && TN)      // bf16 tiles: [bf16(B) 4 KB | bf16(B_lo) 4 KB] behind the fp32 half tile
+                mma_x3bf_block_ts2_tn(d_tmem + (uint32_t)b * L::BN_MAX, a_hi, bb, koff16, desc0_hi, bb + (L::B_HALF_BYTES >> 4),
+                                      bb + (L::B_HALF_BYTES >> 4) + (4096 >> 4), desc_bf_hi, idesc, idesc_bf,
+                                      (kb > kb_beg || j > 0) ? 1u : 0u);
               else if (BF == 1)
                 mma_x3bf_block_ts2(d_tmem, a_hi, bb, bb + (L::B_HALF_BYTES >> 4), desc0_hi, idesc, idesc_bf,
                                    (kb > kb_beg || j > 0) ? 1u : 0u);
@@ -1252,7 +1293,35 @@ gemm_x3ts2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
               uint8_t* bt = smem + stage * STAGE_BYTES + j * SUB_BYTES + A_STAGE_BYTES + b * 2 * L::B_HALF_BYTES;
               const float4* hi = reinterpret_cast<const float4*>(bt);
               float4* lo = reinterpret_cast<float4*>(bt + L::B_HALF_BYTES);
-              if (BF) {
+              if (BF && TN) {
+                // MN-major fp32 boxes [32 k][32 n] (SWIZZLE_128B_ATOM_32B: 32-byte unit u of row k stored at u ^ (k & 3);
+                // box c = n / 32 at + 4096 c) -> bf16 tiles [32 k-rows x 128 B] in the standard 128-byte swizzle
+                // (16-byte chunk j of row k stored at j ^ (k & 7)): a thread converts one 32-byte unit (8 n-values of
+                // one k) into one chunk of bf16(B) and one of bf16(B_lo).  Lane -> (c, u) = lane & 7, k = 4 rows per
+                // warp: a quarter-warp reads 8 distinct 16-byte slots (c = 1 lanes take the upper half first) and
+                // writes the 8 chunks of one row.
+                const int cu = lane & 7, c = cu >> 2, u = cu & 3;
+                const uint32_t src0 = smem_u32(hi) + (uint32_t)c * 4096, dst_hi = smem_u32(lo), dst_lo = dst_hi + 4096;
+#pragma unroll
+                for (int it2 = 0; it2 < 2; ++it2) {
+                  const int k = it2 * 16 + (t >> 5) * 4 + (lane >> 3);
+                  const uint32_t src = src0 + (uint32_t)(k * 128 + ((u ^ (k & 3)) << 5));
+                  const float4 f0 = lds_128(src + (c ? 16u : 0u)), f1 = lds_128(src + (c ? 0u : 16u));
+                  const float4 x = c ? f1 : f0, y = c ? f0 : f1;
+                  const float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+                  uint32_t hb[4], lb[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float a0 = v[2 * e], a1 = v[2 * e + 1];
+                    hb[e] = pack_bf16x2(a0, a1);
+                    lb[e] = pack_bf16x2(a0 - __uint_as_float(__float_as_uint(a0) & 0xFFFFE000u),
+                                        a1 - __uint_as_float(__float_as_uint(a1) & 0xFFFFE000u));
+                  }
+                  const uint32_t off = (uint32_t)(k * 128 + ((cu ^ (k & 7)) << 4));
+                  sts_128(dst_hi + off, hb[0], hb[1], hb[2], hb[3]);
+                  sts_128(dst_lo + off, lb[0], lb[1], lb[2], lb[3]);
+                }
+              } else if (BF) {
                 // row n (128 B, 16-byte chunk c stored at c ^ (n & 7)): fp32 chunks 2d, 2d+1 (k = 8d .. 8d+7) ->
                 // bf16(B) into chunk d and bf16(B_lo) into chunk 4 + d of the same row of the second tile
                 for (int i = t; i < half_bn * 4; i += 128) {
@@ -1965,6 +2034,14 @@ static bool ts_pair_enabled() {
 static bool nt_pair_shape(int M, int N) { return ts_pair_enabled() && M >= 256 && N >= 128 && N % 64 == 0; }
 static bool tn_pair_shape(int Mo, int No) { return ts_pair_enabled() && Mo > 128 && No >= 128 && No % 64 == 0; }
 
+// bf16 cross terms in the weight-gradient (TN) pair kernels: 8 instead of 12 MMA-times per k-block (these kernels run
+// at the tensor pipe's sustained rate, so the executed work is what counts).  Needs the full 128-wide N tile (64 n per
+// CTA = one 128-byte bf16 row per k).  GTS_X3_TN_BF16=0 keeps the all-TF32 form.
+static bool tn_bf_cross(int bn) {
+  static const bool on = !(getenv("GTS_X3_TN_BF16") && atoi(getenv("GTS_X3_TN_BF16")) == 0);
+  return on && bn == 128;
+}
+
 // widest N tile of the A-in-TMEM kernel: 128 (default: 4 stages, overlapped epilogue) or 256 (GTS_X3_BN=256)
 static int ts_bn_cap() {
   static const int cap = (getenv("GTS_X3_BN") && atoi(getenv("GTS_X3_BN")) == 256) ? 256 : 128;
@@ -2075,10 +2152,18 @@ static void tn_plan(int32_t Mo, int32_t No, int64_t K, int32_t mode, tc::Params&
 // workspace: per split one record [Mo*No partial product | Mo (rounded up to 4) partial column sums of A]
 static inline int64_t tn_record(int32_t Mo, int32_t No) { return (int64_t)Mo * No + (((int64_t)Mo + 3) / 4) * 4; }
 
+// A 256-wide product as the two-B form over its two 128-column halves (B1 = B[:, 0:128], B2 = B[:, 128:256]): the split A
+// tile in tensor memory feeds both halves, so A is read once instead of once per N tile, and every cluster owns one
+// K split of the whole product (74 splits instead of 2 x 37).  GTS_X3_TN_HALVES=0 keeps one work item per N tile.
+static bool tn_split_halves(int32_t Mo, int32_t No, int32_t mode) {
+  static const bool on = !(getenv("GTS_X3_TN_HALVES") && atoi(getenv("GTS_X3_TN_HALVES")) == 0);
+  return on && mode == GTS_GEMM_TF32X3 && tc::x3_in_tmem() && No == 256 && tc::tn_pair_shape(Mo, 128) && tc::tn_bf_cross(128);
+}
+
 size_t gemm_tn_tcgen05_ws(int32_t Mo, int32_t No, int64_t K, int32_t mode) {
   if (Mo < 1 || No < 1 || K < 1) return 0;
   tc::Params p{};
-  tn_plan(Mo, No, K, mode, p);
+  tn_plan(Mo, tn_split_halves(Mo, No, mode) ? 128 : No, K, mode, p);
   return align_up((size_t)p.splits * (size_t)tn_record(Mo, No) * sizeof(float), 256);
 }
 
@@ -2090,14 +2175,39 @@ int gemm_tn_tcgen05(const float* A, int64_t lda, const float* B, int64_t ldb, fl
                     cudaStream_t st) {
   using namespace tc;
   const bool x3 = mode == GTS_GEMM_TF32X3;
+  const bool halves = tn_split_halves(Mo, No, mode);
   Params p{};
-  tn_plan(Mo, No, K, mode, p);
+  tn_plan(Mo, halves ? 128 : No, K, mode, p);
   const int64_t record = tn_record(Mo, No);
   const size_t need = align_up((size_t)p.splits * (size_t)record * sizeof(float), 256);
   if (!ws || ws_bytes < need) { set_error("gts_gemm_tn: workspace %zu < required %zu", ws_bytes, need); return GTS_ERR_WORKSPACE; }
-  p.M = Mo; p.N = No;
+  p.M = Mo; p.N = halves ? 128 : No;
   p.C = reinterpret_cast<float*>(ws); p.ldc = No;
   p.split_stride = record;
+  if (halves) {
+    // record = [Mo x 256 product | column sums of A]: the second half tile lands 128 columns to the right
+    p.c2_off = 128;
+    p.colsum_partial = colsum_out ? p.C + (int64_t)Mo * No : nullptr;
+    CUtensorMap tA, tB1, tB2;
+    if (!encode_2d(&tA, A, K, Mo, lda, 32, BK, false, true)) return GTS_ERR_CUDA;
+    if (!encode_2d(&tB1, B, K, 128, ldb, 32, BK, false, true)) return GTS_ERR_CUDA;
+    if (!encode_2d(&tB2, B + 128, K, 128, ldb, 32, BK, false, true)) return GTS_ERR_CUDA;
+    const int n_work_h = p.tiles_m * p.tiles_n * p.splits;
+    int rc_h = launch_ts2<true, true, 1>(tA, tA, tB1, tB2, p, n_work_h, st);
+    if (rc_h != GTS_OK) return rc_h;
+    if (colsum_out && Mo % 4 == 0 && p.splits >= 8 && splitk_reduce_fused_ok(Mo, No, ldc, Mo, record, p.C, C, colsum_out)) {
+      launch_splitk_reduce_fused(p.C, record, p.splits, Mo, No, C, colsum_out, Mo, st);
+      GTS_LAUNCH_CHECK();
+      return GTS_OK;
+    }
+    launch_splitk_reduce(p.C, record, p.splits, Mo, No, C, ldc, st);
+    GTS_LAUNCH_CHECK();
+    if (colsum_out) {
+      launch_splitk_reduce(p.C + (int64_t)Mo * No, record, p.splits, 1, Mo, colsum_out, Mo, st);
+      GTS_LAUNCH_CHECK();
+    }
+    return GTS_OK;
+  }
   const bool in_tmem = x3 && x3_in_tmem();
   if (colsum_out && !in_tmem) { set_error("gts_gemm_tn: fused column sums need the 3xTF32 A-in-TMEM kernel"); return GTS_ERR_INVALID; }
   float* cs_partial = p.C + (int64_t)Mo * No;
@@ -2107,7 +2217,8 @@ int gemm_tn_tcgen05(const float* A, int64_t lda, const float* B, int64_t ldb, fl
   if (!encode_2d(&tB, B, K, No, ldb, 32, BK, !x3, true)) return GTS_ERR_CUDA;
   const int n_work = p.tiles_m * p.tiles_n * p.splits;
   const bool pair = in_tmem && tn_pair_shape(Mo, No);
-  int rc = pair ? launch_ts2<true>(tA, tA, tB, tB, p, n_work, st)
+  int rc = pair ? (tn_bf_cross(p.BN) ? launch_ts2<true, false, 1>(tA, tA, tB, tB, p, n_work, st)
+                                      : launch_ts2<true>(tA, tA, tB, tB, p, n_work, st))
          : in_tmem ? (ts_bn_cap() == 256 ? launch_ts<true, 256>(tA, tA, tB, tB, p, n_work, st)
                                          : launch_ts<true, 128>(tA, tA, tB, tB, p, n_work, st))
                    : (x3 ? launch<true, true>(tA, tA, tB, tB, p, n_work, st) : launch<true, false>(tA, tA, tB, tB, p, n_work, st));
@@ -2161,7 +2272,8 @@ int gemm_tn2_tcgen05(const float* A, int64_t lda, const float* B1, int64_t ldb1,
   if (!encode_2d(&tB1, B1, K, No, ldb1, 32, BK, false, true)) return GTS_ERR_CUDA;
   if (!encode_2d(&tB2, B2, K, No, ldb2, 32, BK, false, true)) return GTS_ERR_CUDA;
   const int n_work = p.tiles_m * p.tiles_n * p.splits;
-  int rc = launch_ts2<true, true>(tA, tA, tB1, tB2, p, n_work, st);
+  int rc = tn_bf_cross(p.BN) ? launch_ts2<true, true, 1>(tA, tA, tB1, tB2, p, n_work, st)
+                             : launch_ts2<true, true>(tA, tA, tB1, tB2, p, n_work, st);
   if (rc != GTS_OK) return rc;
   const bool contiguous = C2 == C1 + prod && ldc == No;
   if (contiguous && colsum_out && p.splits >= 8 && splitk_reduce_fused_ok(2 * Mo, No, ldc, Mo, record, p.C, C1, colsum_out)) {
