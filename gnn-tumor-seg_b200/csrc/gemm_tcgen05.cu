@@ -1587,6 +1587,7 @@ gemm_x3ntw_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);    // provably warp-uniform
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) GTS_TR(7, 0, clock64());     // trace: kernel entry (record 7 = whole-kernel marks)
   const uint32_t rank = cluster_ctarank();           // 0 = leader (issues the MMAs), 1 = peer
   const int cluster_id = blockIdx.x >> 1;
   const int n_clusters = gridDim.x >> 1;
@@ -1618,6 +1619,7 @@ gemm_x3ntw_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
   cluster_sync_all();                                // barriers initialised and TMEM allocated in BOTH CTAs
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 0) GTS_TR(7, 1, clock64());     // trace: set-up done
 
   // work item w -> (pair tile of 256 rows, 256-column tile); tiles_m counts 256-row pair tiles, tiles_n 256-column tiles
   const int n_work = p.tiles_m * p.tiles_n;
@@ -1896,6 +1898,7 @@ gemm_x3ntw_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
 
   tcgen05_fence_before();
   cluster_sync_all();                                // no CTA may exit (or free TMEM) while its peer still uses it
+  if (threadIdx.x == 0) GTS_TR(7, 2, clock64());     // trace: all roles done
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");

@@ -66,6 +66,16 @@ for cta in (0, 1, 74, 75):
                   f"end {rel(r[4])} ready_wait_sum {r[5]}")
         print(f"         tma empty_wait_sum {r[6]} tma_end {rel(r[7])} | epi L: wait {r[9]-r[8]} drain {r[10]-r[9]} "
               f"R: wait {r[12]-r[11]} drain {r[13]-r[12]} done {rel(r[13])} | asplit full_wait {r[14]} afree_wait {r[15]}")
+# whole-kernel marks (record 7): entry -> set-up done -> first MMA item -> last epilogue -> all roles done
+k = t[0::2, 7]
+first = lead_first = t[0::2, 0, 0]
+n_items = [max(i for i in range(7) if t[c, i, 13] or t[c, i, 10]) for c in range(0, CTAS, 2)]
+last_epi = np.array([max(t[c, i, 13], t[c, i, 10]) for c, i in zip(range(0, CTAS, 2), n_items)])
+last_mma = np.array([t[c, i, 4] for c, i in zip(range(0, CTAS, 2), n_items)])
+print(f"kernel marks (median over leaders, clk): entry->setup {np.median(k[:,1]-k[:,0]):.0f}  setup->first item "
+      f"{np.median(first-k[:,1]):.0f}  first item->last MMA issued {np.median(last_mma-first):.0f}  last MMA issued->last epilogue done "
+      f"{np.median(last_epi-last_mma):.0f}  last epilogue->exit {np.median(k[:,2]-last_epi):.0f}  total {np.median(k[:,2]-k[:,0]):.0f}; "
+      f"items per cluster: {sorted(set(int(x)+1 for x in n_items))}")
 # aggregate over leader CTAs
 lead = t[0::2]
 for it in range(5):
