@@ -511,7 +511,13 @@ def run_ours(args):
     ncu = load_ncu_traffic()
     kern["segmax_fwd"]["traffic"] = traffic_of(ncu, "segmax_fwd_pipe")
     kern["segmax_bwd"]["traffic"] = traffic_of(ncu, "segmax_bwd_vec")
-    kern["gemm_concat_k512"]["traffic"] = traffic_of(ncu, "gemm_x3ts2_kernel<0, 0, 1>", "gemm_x3ts2_kernel<0") if args.mode == "tf32x3" else None
+    kern["gemm_concat_k512"]["traffic"] = traffic_of(ncu, "gemm_x3ntw_kernel") if args.mode == "tf32x3" else None
+    if args.mode == "tf32x3":
+        for nm, d_ in ncu.items():           # tensor-pipe utilisation of the same ncu capture (profiles/r02_ncu_traffic.json)
+            if "gemm_x3ntw_kernel" in nm and "tensor_pipe_pct_of_elapsed" in d_:
+                kern["gemm_concat_k512"]["ncu"] = {"tensor_pipe_pct_of_elapsed": d_["tensor_pipe_pct_of_elapsed"],
+                                                   "sm_clock_ghz": d_.get("sm_clock_ghz"), "dram_pct": d_.get("dram_pct"),
+                                                   "lts_pct": d_.get("lts_pct"), "duration_us": d_.get("duration_us")}
     tot = sum(v["ms"] for v in breakdown.values()) or 1.0
     share = {k: {"ms": round(v["ms"], 4), "calls": v["calls"], "share": round(v["ms"] / tot, 4)}
              for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])}

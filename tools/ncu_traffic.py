@@ -28,6 +28,13 @@ KEEP = {
     "launch__block_size": "block",
     "smsp__inst_executed.sum": "warp_insts",
     "sm__cycles_elapsed.max": "cycles",
+    # tensor-pipe utilisation (the north star asks for it beside the GEMMs) and the L2 / shared-memory pressure
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed": "tensor_pipe_pct_of_elapsed",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pipe_pct_of_active",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed": "lts_pct",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed": "smem_lsu_wavefront_pct",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum": "smem_bank_conflicts",
+    "sm__cycles_elapsed.avg.per_second": "sm_clock_ghz",
 }
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
 
