@@ -330,7 +330,7 @@ def run_ours(args):
     # (model/gnn_model.py:41-47) with its hyper-parameters (lr 1e-4, weight decay 1e-4)
     from gnn_tumor_seg_b200.trainer import FusedAdamW, GraphedStep, SageTrainer
     if args.model == "sage":
-        trainer = SageTrainer(net, class_w, lr=1e-4, weight_decay=1e-4)
+        trainer = SageTrainer(net, class_w, lr=1e-4, weight_decay=1e-4, n_buckets=int(os.environ.get("GTS_DP_BUCKETS", "2")))
 
         def train_step(bg, f, l):
             return trainer.step(bg, f, l)
@@ -383,20 +383,15 @@ def run_ours(args):
     #      the host reads step i's loss (pinned, D2H'd behind the step) after it has enqueued step i+1;
     #  "eager" (N > 1, GAT): the same pipeline without the CUDA graph (in-stream .to(device));
     #  "sync": the reference's blocking loss.item() per step (model/gnn_model.py:43) — GTS_BENCH_E2E=sync.
-    e2e_mode = os.environ.get("GTS_BENCH_E2E", "graph" if (world == 1 and args.model == "sage") else "eager")
+    e2e_mode = os.environ.get("GTS_BENCH_E2E", "graph" if args.model == "sage" else "eager")
     K = 8
     loss_host = torch.zeros(K, dtype=torch.float32).pin_memory()
     loss_ev = [torch.cuda.Event() for _ in range(K)]
     gsteps, copy_stream = None, None
     staged = None
     if e2e_mode == "graph":
-        try:
-            gsteps = [GraphedStep(trainer, *pinned[k]) for k in range(len(pinned))]
-            copy_stream = torch.cuda.Stream(device=dev)
-        except Exception as e:        # e.g. a collective that cannot be captured on this stack: same pipeline, eager body
-            if rank == 0:
-                print("CUDA-graph capture failed (%r): falling back to the eager pipeline" % (e,), file=sys.stderr)
-            gsteps, e2e_mode = None, "eager"
+        gsteps = [GraphedStep(trainer, *pinned[k]) for k in range(len(pinned))]
+        copy_stream = torch.cuda.Stream(device=dev)
     if e2e_mode == "eager" and args.model == "sage":
         # same pipeline, step enqueued eagerly (NCCL collectives inside): static input buffers + copy-stream staging
         staged = [GraphedStep(trainer, *pinned[k], capture=False) for k in range(len(pinned))]
@@ -591,14 +586,15 @@ def run_ours(args):
                 "mode": e2e_mode,
                 "loss_read": {"graph": "every step's loss D2H-copied into pinned memory behind the step and read by the host one "
                                        "step later (while the next step runs); H2D of step i+1 on a copy stream; step replayed "
-                                       "from a CUDA graph (trainer.GraphedStep)",
+                                       "from a CUDA graph (trainer.GraphedStep; N > 1: graph segments around the eager all-reduces)",
                               "eager": "every step's loss D2H-copied into pinned memory and read by the host one step later; "
                                        "H2D of step i+1 on a copy stream into static device buffers (SAGE) / in-stream .to(device) (GAT)",
                               "sync": "one blocking loss.item() per step"}[e2e_mode]},
         "gpu_launches": int(launches),
         "eager_ms_per_step": ms_eager,
-        "value_path": ("CUDA-graph replay of the step (trainer.GraphedStep, incl. the device CSR build), inputs resident in "
-                       "their static device buffers" if gsteps is not None else "eager trainer step, inputs and CSR resident"),
+        "value_path": (("CUDA-graph replay of the step (trainer.GraphedStep, incl. the device CSR build), inputs resident in "
+                        "their static device buffers" + ("" if world == 1 else "; data parallel: captured segments with the eager "
+                        "bucketed NCCL all-reduces between them")) if gsteps is not None else "eager trainer step, inputs and CSR resident"),
         "roofline": roofline,
         "kernels": kern,
         "step_breakdown": share,

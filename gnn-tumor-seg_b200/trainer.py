@@ -292,6 +292,26 @@ class SageTrainer:
         ops._count(23 * L + 3)
         return self.arena.extra[0] / self.arena.extra[1]
 
+    # ---- the data-parallel step as phases (GraphedStep captures each into its own CUDA graph; the NCCL calls between
+    #      them stay eager) ---------------------------------------------------------------------------------------
+    def dp_phase_first(self, graph, feats, labels):
+        """forward + CE + backward of the top bucket's layers."""
+        hi0, lo0, _, _ = self.buckets[0]
+        self._dp_args = self._step_args(graph, feats, labels, False, lo0)
+        check(_lib.load().gts_sage_step(C.byref(self._dp_args), stream_ptr()), "gts_sage_step")
+        ops._count(23 * self.L + 3)
+
+    def dp_phase_rest(self, i):
+        """backward of bucket i (i >= 1)."""
+        hi, lo, _, _ = self.buckets[i]
+        check(_lib.load().gts_sage_step_backward_rest(C.byref(self._dp_args), hi, lo, stream_ptr()), "gts_sage_step_backward_rest")
+
+    def dp_all_reduce(self, i):
+        """async NCCL all-reduce of bucket i's gradient range (bucket 0 carries the two loss sums)."""
+        _, _, g_lo, g_hi = self.buckets[i]
+        end = self.arena.total + 2 if i == 0 else g_hi
+        return dist.all_reduce(self.arena.grads[g_lo:end], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+
     @property
     def denominator(self):
         """sum of the class weights of the (global) batch — 1-element device tensor."""
@@ -310,14 +330,12 @@ class GraphedStep:
 
     def __init__(self, trainer: SageTrainer, host_graph, feats, labels, capture: bool = True):
         """capture=False keeps the static input buffers and the copy-stream staging but runs the step eagerly on
-        replay (data-parallel steps: the NCCL collectives stay outside CUDA graphs)."""
+        replay.  With a data-parallel trainer the step is captured as segments around the eager NCCL all-reduces."""
         from .graph import BatchedGraph
-        if trainer.world_size != 1 and capture:
-            # tried on 2 x B200 (torch 2.11 / NCCL 2.28): capturing the async bucketed all-reduces hung the ranks
-            raise GtsError("GraphedStep: single-device steps only (collectives stay on the eager path: capture=False)")
         self.trainer = trainer
         self._BatchedGraph = BatchedGraph
         self.graph = None
+        self.segments = None
         dev = trainer.arena.params.device
         self.signature = self.signature_of(host_graph, feats)
         self.src = torch.empty_like(host_graph._src, device=dev)
@@ -338,9 +356,34 @@ class GraphedStep:
             self._body(BatchedGraph)
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._body(BatchedGraph)
+        if trainer.world_size == 1:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._body(BatchedGraph)
+            return
+        # Data parallel: the NCCL all-reduces stay OUTSIDE the graphs (capturing the async collectives hung the ranks on
+        # 2 x B200, torch 2.11 / NCCL 2.28).  The step becomes captured segments with the eager collectives between
+        # them: [CSR build + forward + CE + backward of the top bucket] | all-reduce | [backward of bucket i] | all-reduce
+        # ... | [AdamW + loss]; every rank replays the same sequence.
+        pool = torch.cuda.graph_pool_handle()
+        self.segments = []
+        g0 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g0, pool=pool):
+            self.device_graph = BatchedGraph.from_device_edges(self.src, self.dst, self.node_off, self.edge_off,
+                                                               self._node_counts, self._edge_counts)
+            trainer.dp_phase_first(self.device_graph, self.feats, self.labels)
+        self.segments.append(g0)
+        for i in range(1, len(trainer.buckets)):
+            gi = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gi, pool=pool):
+                trainer.dp_phase_rest(i)
+            self.segments.append(gi)
+        self._dp_args = trainer._dp_args                  # the phases' argument block (pointers into static buffers)
+        gl = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gl, pool=pool):
+            trainer.optimizer.step(grad_denom=trainer.denominator)
+            self.loss.copy_(trainer.arena.extra[0] / trainer.arena.extra[1])
+        self.segments.append(gl)
 
     @staticmethod
     def signature_of(host_graph, feats):
@@ -380,6 +423,16 @@ class GraphedStep:
         self.trainer.optimizer._sync_lr()
         if self.graph is not None:
             self.graph.replay()
+        elif self.segments is not None:
+            tr = self.trainer
+            tr._dp_args = self._dp_args
+            works = []
+            for i in range(len(tr.buckets)):
+                self.segments[i].replay()
+                works.append(tr.dp_all_reduce(i))        # NCCL stream; the next segment runs beside it
+            for w in works:
+                w.wait()
+            self.segments[-1].replay()
         else:
             self._body(self._BatchedGraph)
         self._done = torch.cuda.Event()

@@ -64,7 +64,29 @@ def _worker(rank, world, port, out_dir):
     tr1.optimizer.step()
     torch.cuda.synchronize()
     prel = float((tr.arena.params - tr1.arena.params).abs().max())
-    torch.save({"bitwise": bitwise, "rel": rel, "loss": float(loss), "loss1": float(loss1), "prel": prel},
+    # the same data-parallel step replayed from CUDA-graph segments (trainer.GraphedStep) vs eager: 3 steps each
+    from gnn_tumor_seg_b200.trainer import GraphedStep
+    sel = [graphs[i] for i in range(rank, 4, world)]
+    hg = G.batch([G.from_edge_list(g.src, g.dst, g.n_nodes) for g in sel], pin=True)
+    hx = torch.as_tensor(np.concatenate([g.features for g in sel])).pin_memory()
+    hy = torch.as_tensor(np.concatenate([g.labels for g in sel])).pin_memory()
+    nets = []
+    for _ in range(2):
+        torch.manual_seed(5)
+        nets.append(networks.GraphSage(20, [256, 256, 64], 4, "pool", 0).to(dev))
+    tr_e = SageTrainer(nets[0], w, lr=1e-3, weight_decay=1e-4)
+    tr_g = SageTrainer(nets[1], w, lr=1e-3, weight_decay=1e-4)
+    gs = GraphedStep(tr_g, hg, hx, hy)                      # one eager warm-up step + capture of the segments
+    assert gs.segments is not None and len(gs.segments) == len(tr_g.buckets) + 1
+    le = lg = None
+    for it in range(3):
+        le = tr_e.step(hg.to(dev), hx.to(dev), hy.to(dev))
+        if it > 0:
+            lg = gs(hg, hx, hy)
+    torch.cuda.synchronize()
+    gdiff = float((tr_e.arena.params - tr_g.arena.params).abs().mean())
+    torch.save({"bitwise": bitwise, "rel": rel, "loss": float(loss), "loss1": float(loss1), "prel": prel,
+                "graph_param_diff": gdiff, "loss_eager": float(le), "loss_graph": float(lg)},
                os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
@@ -81,3 +103,4 @@ def test_two_rank_nccl_step_equals_single_device_union_batch(tmp_path):
         assert d["rel"] <= 1e-5, d
         assert abs(d["loss"] - d["loss1"]) <= 1e-5 * abs(d["loss1"]), d
         assert d["prel"] <= 2e-4, d          # |lr| = 1e-3: a first AdamW step moves every element by ~lr
+        assert d["graph_param_diff"] < 1e-6 and abs(d["loss_eager"] - d["loss_graph"]) <= 1e-5 * abs(d["loss_eager"]), d
