@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GTS_LIB_PATH") or os.path.join(_HERE, "libgts.so")     # override: A/B builds of the library
 
 GTS_OK = 0
-ACT_NONE, ACT_RELU, ACT_MASK_POS, ACT_MASK_POS_SCATTER = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_MASK_POS, ACT_MASK_POS_SCATTER, ACT_MASK_BITS = 0, 1, 2, 3, 4
 GEMM_FP32, GEMM_TF32, GEMM_TF32X3 = 0, 1, 2
 GEMM_MODES = {"fp32": GEMM_FP32, "tf32": GEMM_TF32, "tf32x3": GEMM_TF32X3}
 
@@ -40,6 +40,8 @@ class GemmNtArgs(C.Structure):
         ("bias2", C.c_void_p),
         ("scatter_idx", C.c_void_p), ("ld_idx", C.c_int64),
         ("scatter_out", C.c_void_p), ("ld_out", C.c_int64),
+        ("relu_bits_out", C.c_void_p), ("ld_bits_out", C.c_int64),
+        ("aux_bits", C.c_void_p), ("ld_aux_bits", C.c_int64),
     ]
 
 
@@ -80,6 +82,7 @@ _SIGNATURES = {
                                 C.c_void_p, C.c_size_t, c_stream]),
     "gts_edge_perm_compose": (C.c_int, [c_i32p, c_i32p, C.c_int64, c_i32p, c_i32p, c_stream]),
     "gts_gemm_nt": (C.c_int, [C.POINTER(GemmNtArgs), c_stream]),
+    "gts_gemm_nt_bits_supported": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     "gts_gemm_tn_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64, C.c_int32]),
     "gts_gemm_tn": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_int32, C.c_int32,
                               C.c_int64, C.c_int32, C.c_void_p, C.c_size_t, c_stream]),
@@ -94,6 +97,9 @@ _SIGNATURES = {
     "gts_transpose": (C.c_int, [c_f32p, C.c_int64, C.c_int32, C.c_int32, c_f32p, C.c_int64, c_stream]),
     "gts_segmax_fwd": (C.c_int, [c_f32p, C.c_int64, c_i32p, c_i32p, C.c_int32, C.c_int32, c_f32p, C.c_int64,
                                  c_i32p, C.c_int64, c_stream]),
+    "gts_segmax_fwd_bits_supported": (C.c_int, [C.c_int32, C.c_int32, C.c_int64]),
+    "gts_segmax_fwd_bits": (C.c_int, [c_f32p, C.c_int64, c_i32p, c_i32p, C.c_int32, C.c_int32, c_f32p, C.c_int64,
+                                      c_i32p, C.c_int64, C.c_void_p, C.c_int64, c_stream]),
     "gts_segmax_bwd": (C.c_int, [c_f32p, C.c_int64, c_i32p, C.c_int64, C.c_int32, C.c_int32, c_f32p, C.c_int64,
                                  C.c_int32, c_stream]),
     "gts_segmax_bwd_det": (C.c_int, [c_f32p, C.c_int64, c_i32p, C.c_int64, c_i32p, c_i32p, C.c_int32, C.c_int32,

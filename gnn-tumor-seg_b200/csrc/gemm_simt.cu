@@ -21,6 +21,7 @@ int gemm_tn2_tcgen05(const float* A, int64_t lda, const float* B1, int64_t ldb1,
                      void* ws, size_t ws_bytes, cudaStream_t st);
 size_t gemm_tn_tcgen05_ws(int32_t Mo, int32_t No, int64_t K, int32_t mode);
 bool gemm_nt_tcgen05_supported(const gts_gemm_nt_args* a);
+bool gemm_nt_bits_supported(int32_t M, int32_t N, int32_t mode);
 bool gemm_tn_tcgen05_supported(const float* A, int64_t lda, const float* B, int64_t ldb, int32_t Mo, int32_t No, int64_t K);
 
 constexpr int kSimtThreads = 256;
@@ -463,8 +464,14 @@ int gts_gemm_nt(const gts_gemm_nt_args* a, gts_stream_t stream) {
   GTS_CHECK_ARG(a->act != GTS_ACT_MASK_POS_SCATTER || (a->scatter_idx && a->scatter_out && a->aux),
                 "gts_gemm_nt: GTS_ACT_MASK_POS_SCATTER needs aux, scatter_idx and scatter_out");
   GTS_CHECK_ARG(a->K1 == 0 || (a->A1 && a->B1), "gts_gemm_nt: A1/B1 null with K1 > 0");
-  GTS_CHECK_ARG(a->act >= GTS_ACT_NONE && a->act <= GTS_ACT_MASK_POS_SCATTER, "gts_gemm_nt: unknown act %d", a->act);
+  GTS_CHECK_ARG(a->act >= GTS_ACT_NONE && a->act <= GTS_ACT_MASK_BITS, "gts_gemm_nt: unknown act %d", a->act);
   GTS_CHECK_ARG(a->act != GTS_ACT_MASK_POS || a->aux != nullptr, "gts_gemm_nt: GTS_ACT_MASK_POS needs aux");
+  const bool bits = a->act == GTS_ACT_MASK_BITS || a->relu_bits_out != nullptr;
+  if (bits && !(gemm_nt_bits_supported(a->M, a->N, a->mode) && gemm_nt_tcgen05_supported(a))) {
+    set_error("gts_gemm_nt: bit-matrix masks (GTS_ACT_MASK_BITS / relu_bits_out) are not supported for M=%d N=%d mode=%d "
+              "(see gts_gemm_nt_bits_supported)", a->M, a->N, a->mode);
+    return GTS_ERR_UNSUPPORTED;
+  }
   cudaStream_t st = as_stream(stream);
   if (a->mode == GTS_GEMM_FP32) return gemm_nt_simt(a, st);
   if (a->mode == GTS_GEMM_TF32 || a->mode == GTS_GEMM_TF32X3) {
@@ -474,6 +481,8 @@ int gts_gemm_nt(const gts_gemm_nt_args* a, gts_stream_t stream) {
   set_error("gts_gemm_nt: unknown mode %d", a->mode);
   return GTS_ERR_INVALID;
 }
+
+int gts_gemm_nt_bits_supported(int32_t M, int32_t N, int32_t mode) { return gemm_nt_bits_supported(M, N, mode) ? 1 : 0; }
 
 size_t gts_gemm_tn_workspace_bytes(int32_t Mo, int32_t No, int64_t K, int32_t mode) {
   if (Mo <= 0 || No <= 0 || K <= 0) return 256;

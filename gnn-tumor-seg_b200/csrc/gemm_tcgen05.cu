@@ -219,6 +219,8 @@ struct Params {
   int splits; int kb_per_split; int kb_total; int64_t split_stride;
   int64_t c2_off;          // TN two-B form: offset (floats) of the second product inside a split record
   float* colsum_partial;   // TN, A-in-TMEM kernel: [splits][M] column sums of the A operand (or null)
+  uint32_t* bits_out; int64_t ld_bits_out;            // wide NT kernel: bit matrix of (C > 0) beside a ReLU output (or null)
+  const uint32_t* aux_bits; int64_t ld_aux_bits;      // wide NT kernel, GTS_ACT_MASK_BITS: the mask as a bit matrix
   long long* trace;        // GTS_TRACE builds only: per-CTA clock64 records of gemm_x3ntw_kernel (tools/gemm_trace.py)
   int dbg;                 // GTS_TRACE builds only: ablation switches
 };
@@ -1418,6 +1420,11 @@ __device__ __forceinline__ void epilogue_half_regs(const Params& p, uint32_t t_b
                                                    uint32_t empty_remote, bool leader) {
   const int cc = (lane & 7) * 4;
   const int rsub = lane >> 3;
+  // rows of this 32-row group inside M (32 everywhere but in the last tile); row 4j + rsub is valid iff j < jmax
+  // (the float-mask form holds 64 more registers for its double-buffered operand: it takes full row groups only, the
+  // caller sends partial ones through the generic path — with the predication it spilled 110 registers)
+  const int nrows = min(32, p.M - m0);
+  const int jmax = ACT == GTS_ACT_MASK_POS ? 8 : (nrows > rsub ? (nrows - rsub + 3) >> 2 : 0);
   // explicit shared-state-space addresses: through a generic float* the compiler emitted generic LD / ST for the staging
   // tile, which queue behind the outstanding global loads of the mask operand (seen: 14 000+ clk per masked half tile)
   const uint32_t stg_w = smem_u32(stg) + (uint32_t)(lane * EPI_LD) * 4;                 // this lane's row (write side)
@@ -1426,7 +1433,7 @@ __device__ __forceinline__ void epilogue_half_regs(const Params& p, uint32_t t_b
   const int step4 = 4 * (int)p.ldc;                                    // 32-bit element offsets: one IMAD.WIDE per access
   const float* a_row = ACT == GTS_ACT_MASK_POS ? p.aux + (int64_t)(m0 + rsub) * p.ldc + n0 + cc : nullptr;   // ldaux == ldc
   float4 b[4];
-  if (ACT != GTS_ACT_MASK_POS) {
+  if (ACT == GTS_ACT_NONE || ACT == GTS_ACT_RELU) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       b[c] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1437,13 +1444,24 @@ __device__ __forceinline__ void epilogue_half_regs(const Params& p, uint32_t t_b
       }
     }
   }
-  // mask operand: two register sets, the loads of chunk c+1 all issued before chunk c is stored.  (Refilling aux[j]
-  // right after its use — one register set — serialised on the scoreboard: every LDS of the store loop then waited
-  // for the previous row's global load, 21 000 clk per half tile.)
+  // mask operand (float form): two register sets, the loads of chunk c+1 all issued before chunk c is stored.  (Refilling
+  // aux[j] right after its use — one register set — serialised on the scoreboard: every LDS of the store loop then
+  // waited for the previous row's global load, 21 000 clk per half tile.)
   float4 aux[2][8];
   if (ACT == GTS_ACT_MASK_POS) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) aux[0][j] = ldg_nc_na(reinterpret_cast<const float4*>(a_row + j * step4));
+    for (int j = 0; j < 8; ++j)
+      aux[0][j] = j < jmax ? ldg_nc_na(reinterpret_cast<const float4*>(a_row + j * step4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // mask operand (bit form): the four words (one per 32-column chunk of this half tile) of each of this lane's 8 rows,
+  // fetched before the accumulator is even complete
+  uint4 mw[8];
+  if (ACT == GTS_ACT_MASK_BITS) {
+    const uint32_t* brow = p.aux_bits + (int64_t)(m0 + rsub) * p.ld_aux_bits + (n0 >> 5);
+    const int64_t bstep4 = 4 * p.ld_aux_bits;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      mw[j] = j < jmax ? *reinterpret_cast<const uint4*>(brow + j * bstep4) : make_uint4(0u, 0u, 0u, 0u);
   }
   mbar_wait(full_bar, full_phase);
   tcgen05_fence_after();
@@ -1454,12 +1472,14 @@ __device__ __forceinline__ void epilogue_half_regs(const Params& p, uint32_t t_b
   tcgen05_fence_before();
   __syncwarp();
   if (lane == 0) { if (leader) mbar_arrive(empty_local); else mbar_arrive_remote(empty_remote); }   // accumulator free again
+  uint32_t* bits_row = (ACT == GTS_ACT_RELU && p.bits_out) ? p.bits_out + (int64_t)(m0 + rsub) * p.ld_bits_out + (n0 >> 5) : nullptr;
+  const int64_t bits_step4 = 4 * p.ld_bits_out;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     if (ACT == GTS_ACT_MASK_POS && c < 3) {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        aux[(c + 1) & 1][j] = ldg_nc_na(reinterpret_cast<const float4*>(a_row + j * step4 + 32 * (c + 1)));
+        if (j < jmax) aux[(c + 1) & 1][j] = ldg_nc_na(reinterpret_cast<const float4*>(a_row + j * step4 + 32 * (c + 1)));
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -1472,13 +1492,27 @@ __device__ __forceinline__ void epilogue_half_regs(const Params& p, uint32_t t_b
         const float4 a = aux[c & 1][j];
         x.x = a.x > 0.f ? x.x : 0.f; x.y = a.y > 0.f ? x.y : 0.f;
         x.z = a.z > 0.f ? x.z : 0.f; x.w = a.w > 0.f ? x.w : 0.f;
+      } else if (ACT == GTS_ACT_MASK_BITS) {
+        // bit 8 * comp + (lane & 7) of the chunk's word <-> column 4 * (lane & 7) + comp
+        const uint32_t w = (c == 0 ? mw[j].x : c == 1 ? mw[j].y : c == 2 ? mw[j].z : mw[j].w) >> (lane & 7);
+        x.x = (w & 0x1u) ? x.x : 0.f; x.y = (w & 0x100u) ? x.y : 0.f;
+        x.z = (w & 0x10000u) ? x.z : 0.f; x.w = (w & 0x1000000u) ? x.w : 0.f;
       } else {
         x.x += b[c].x; x.y += b[c].y; x.z += b[c].z; x.w += b[c].w;
         if (ACT == GTS_ACT_RELU) {
           x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
         }
       }
-      if (!GTS_DBG(0)) *reinterpret_cast<float4*>(c_row + j * step4 + 32 * c) = x;
+      if (ACT == GTS_ACT_RELU && bits_row) {
+        // the ReLU mask of this output as bits, for the backward's data-gradient GEMM: lanes 8 * rsub .. + 7 hold the 32
+        // columns of row 4j + rsub; byte rsub of each component's ballot, component-major, is that row's word
+        const uint32_t b0 = __ballot_sync(0xffffffffu, x.x > 0.f), b1 = __ballot_sync(0xffffffffu, x.y > 0.f);
+        const uint32_t b2 = __ballot_sync(0xffffffffu, x.z > 0.f), b3 = __ballot_sync(0xffffffffu, x.w > 0.f);
+        const uint32_t sel = (uint32_t)rsub | ((4u + (uint32_t)rsub) << 4);
+        const uint32_t w01 = __byte_perm(b0, b1, sel), w23 = __byte_perm(b2, b3, sel);
+        if ((lane & 7) == 0 && j < jmax) bits_row[j * bits_step4 + c] = __byte_perm(w01, w23, 0x5410);
+      }
+      if (j < jmax && !GTS_DBG(0)) *reinterpret_cast<float4*>(c_row + j * step4 + 32 * c) = x;
     }
     __syncwarp();
   }
@@ -1873,19 +1907,24 @@ gemm_x3ntw_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
           mbar_wait(&tmem_full[acc], full_phase);
           if (lane == 0) GTS_TR((int)(h >> 1), 9 + 3 * half, clock64());
         }
-        if (fast_ok && m0 + 32 <= p.M) {
-          // whole slice into registers, accumulator released inside, stores afterwards
-          if (p.act == GTS_ACT_MASK_POS)
-            epilogue_half_regs<GTS_ACT_MASK_POS>(p, t_base, m0, n0, stg, lane, &tmem_full[acc], full_phase, &tmem_empty[acc],
-                                                 tmem_empty_leader + acc * 8, rank == 0);
-          else if (p.act == GTS_ACT_RELU)
-            epilogue_half_regs<GTS_ACT_RELU>(p, t_base, m0, n0, stg, lane, &tmem_full[acc], full_phase, &tmem_empty[acc],
-                                             tmem_empty_leader + acc * 8, rank == 0);
-          else
-            epilogue_half_regs<GTS_ACT_NONE>(p, t_base, m0, n0, stg, lane, &tmem_full[acc], full_phase, &tmem_empty[acc],
-                                             tmem_empty_leader + acc * 8, rank == 0);
+        if (fast_ok && m0 < p.M && (p.act != GTS_ACT_MASK_POS || m0 + 32 <= p.M)) {
+          // whole slice into registers, accumulator released inside, stores afterwards (partial row groups predicated)
+#define GTS_EPI(ACT_) epilogue_half_regs<ACT_>(p, t_base, m0, n0, stg, lane, &tmem_full[acc], full_phase, &tmem_empty[acc], \
+                                               tmem_empty_leader + acc * 8, rank == 0)
+          if (p.act == GTS_ACT_MASK_POS) GTS_EPI(GTS_ACT_MASK_POS);
+          else if (p.act == GTS_ACT_MASK_BITS) GTS_EPI(GTS_ACT_MASK_BITS);
+          else if (p.act == GTS_ACT_RELU) GTS_EPI(GTS_ACT_RELU);
+          else GTS_EPI(GTS_ACT_NONE);
+#undef GTS_EPI
+        } else if (fast_ok && m0 >= p.M) {
+          // row group entirely beyond M (last tile): nothing to store, only the accumulator hand-back
+          mbar_wait(&tmem_full[acc], full_phase);
+          tcgen05_fence_after();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (rank == 0) mbar_arrive(&tmem_empty[acc]); else mbar_arrive_remote(tmem_empty_leader + acc * 8); }
         } else {
-          // partial row group (last M tile) or a mask operand with its own leading dimension: generic chunk-wise path
+          // a float mask operand with its own leading dimension: generic chunk-wise path
           epilogue_tile<false>(p, t_base, m0, n0, p.C, stg, lane, 0, 32, masked, &tmem_full[acc], full_phase);
           tcgen05_fence_before();
           __syncwarp();
@@ -2064,6 +2103,14 @@ static int pick_bn(int n, int granule, int cap = MAX_BN) {
 
 }  // namespace tc
 
+// the shapes / modes the 256-wide kernel takes (mirrors the dispatch in gemm_nt_tcgen05)
+bool gemm_nt_bits_supported(int32_t M, int32_t N, int32_t mode) {
+  static const bool ntw_on = !(getenv("GTS_X3_NTW") && atoi(getenv("GTS_X3_NTW")) == 0);
+  static const int bf_cross = getenv("GTS_X3_BF16") ? atoi(getenv("GTS_X3_BF16")) : 1;
+  return mode == GTS_GEMM_TF32X3 && tc::x3_in_tmem() && tc::nt_pair_shape(M, N) && ntw_on && bf_cross == 1 && N % 256 == 0 &&
+         tc::get_encode() != nullptr;
+}
+
 bool gemm_nt_tcgen05_supported(const gts_gemm_nt_args* a) {
   if (a->M < 1 || a->N < 4 || a->N % 4 != 0) return false;
   if (a->K1 < 1 || !tc::operand_ok(a->A1, a->lda1) || !tc::operand_ok(a->B1, a->ldb1)) return false;
@@ -2074,6 +2121,8 @@ bool gemm_nt_tcgen05_supported(const gts_gemm_nt_args* a) {
   if (a->bias && !tc::al16(a->bias)) return false;
   if (a->bias2 && !tc::al16(a->bias2)) return false;
   if (a->act == GTS_ACT_MASK_POS && (!tc::al16(a->aux) || a->ldaux % 4 != 0)) return false;
+  if (a->act == GTS_ACT_MASK_BITS && (!a->aux_bits || !tc::al16(a->aux_bits) || a->ld_aux_bits % 4 != 0)) return false;
+  if (a->relu_bits_out && (a->act != GTS_ACT_RELU || a->ld_bits_out < a->N / 32)) return false;
   return tc::get_encode() != nullptr;
 }
 
@@ -2098,6 +2147,7 @@ int gemm_nt_tcgen05(const gts_gemm_nt_args* a, cudaStream_t st) {
   p.kb1 = (a->K1 + BK - 1) / BK;
   p.kb2 = two ? (a->K2 + BK - 1) / BK : 0;
   p.bias = a->bias; p.bias2 = a->bias2; p.aux = a->aux; p.ldaux = a->ldaux; p.act = a->act;
+  p.bits_out = a->relu_bits_out; p.ld_bits_out = a->ld_bits_out; p.aux_bits = a->aux_bits; p.ld_aux_bits = a->ld_aux_bits;
   p.splits = 1;
   CUtensorMap tA1, tA2, tB1, tB2;
   if (!encode_2d(&tA1, a->A1, a->M, a->K1, a->lda1, BK, BM, rnd)) return GTS_ERR_CUDA;
@@ -2114,6 +2164,10 @@ int gemm_nt_tcgen05(const gts_gemm_nt_args* a, cudaStream_t st) {
   // Measured: same error against fp64 (2.7e-6 max on K=256 products, logits 2.6e-5 on the 8-layer stack), K=256
   // 59.8 -> 55.9 us, K=512 100.6 -> 98.3 us, training step 5.19 -> 5.10 ms.
   if (wide) return launch_ntw(tA1, tA2, tB1, tB2, p, n_work, st);
+  if (a->relu_bits_out || a->act == GTS_ACT_MASK_BITS) {
+    set_error("gts_gemm_nt: bit-matrix masks need the 256-wide CTA-pair kernel (gts_gemm_nt_bits_supported)");
+    return GTS_ERR_UNSUPPORTED;
+  }
   if (pair && bf_cross == 2) return launch_ts2<false, false, 2>(tA1, tA2, tB1, tB2, p, n_work, st);
   if (pair && bf_cross == 1) return launch_ts2<false, false, 1>(tA1, tA2, tB1, tB2, p, n_work, st);
   if (pair) return launch_ts2<false>(tA1, tA2, tB1, tB2, p, n_work, st);

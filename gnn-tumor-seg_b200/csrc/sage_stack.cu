@@ -3,6 +3,7 @@
 // orchestration of the K1/K2/K3 kernels: every launch goes to the caller's
 // stream, all scratch is carved from the caller's workspace.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace gts {
 
@@ -13,6 +14,9 @@ struct StackPlan {
   size_t neigh[kMaxLayers], arg[kMaxLayers], out[kMaxLayers];
   size_t P = 0, g0 = 0, g1 = 0, dP = 0, gemm_ws = 0, colsum_ws = 0, dlogits = 0;
   size_t wnT[kMaxLayers], wsT[kMaxLayers], wpT[kMaxLayers];      // transposed weights of every layer (one batched launch)
+  // ReLU masks as bit matrices (1 bit per element): neigh_bits[l] = (neigh_l > 0) written by the seg-max forward,
+  // out_bits[l] = (out_l > 0) written by the concat GEMM's epilogue; 0 = not available for that layer (float mask then)
+  size_t neigh_bits[kMaxLayers], out_bits[kMaxLayers];
   size_t gemm_ws_bytes = 0, colsum_ws_bytes = 0;
   size_t total = 0;
 };
@@ -32,10 +36,17 @@ static bool make_plan(const gts_sage_layer* layers, int L, int64_t N, bool train
   }
   const size_t n = (size_t)N;
   if (training) {
+    static const bool bits_on = !(getenv("GTS_MASK_BITS") && atoi(getenv("GTS_MASK_BITS")) == 0);
     for (int l = 0; l < L; ++l) {
       pl.neigh[l] = take(n * layers[l].din * 4);
       pl.arg[l] = take(n * layers[l].din * 4);
       pl.out[l] = (l + 1 < L) ? take(n * layers[l].dout * 4) : 0;
+      // bit masks where both the producer and the consumer (256-wide CTA-pair GEMM) support them
+      const bool nb = bits_on && gts_segmax_fwd_bits_supported((int32_t)N, layers[l].din, layers[l].din) &&
+                      gts_gemm_nt_bits_supported((int32_t)N, layers[l].din, mode);
+      pl.neigh_bits[l] = nb ? take(n * (layers[l].din / 32) * 4) : 0;
+      const bool ob = bits_on && l + 1 < L && layers[l].relu && gts_gemm_nt_bits_supported((int32_t)N, layers[l].dout, mode);
+      pl.out_bits[l] = ob ? take(n * (layers[l].dout / 32) * 4) : 0;
     }
     pl.P = take(n * max_din * 4);        // forward: pooled features; backward: dNeigh'
     pl.g0 = take(n * max_dim * 4);       // backward: dZ / dh ping-pong
@@ -59,6 +70,7 @@ static bool make_plan(const gts_sage_layer* layers, int L, int64_t N, bool train
     pl.colsum_ws = take(cw);
     pl.dlogits = take(n * layers[L - 1].dout * 4);     // gts_sage_step: gradient of the loss w.r.t. the logits
   } else {
+    for (int l = 0; l < L; ++l) pl.neigh_bits[l] = pl.out_bits[l] = 0;
     pl.P = take(n * max_din * 4);
     pl.neigh[0] = take(n * max_din * 4);      // single reused neigh buffer
     pl.g0 = take(n * max_dim * 4);            // activations ping-pong
@@ -78,9 +90,11 @@ static inline float* at(void* ws, size_t off) { return reinterpret_cast<float*>(
 
 static int nt(const float* A1, int64_t lda1, int K1, const float* B1, int64_t ldb1, const float* A2, int64_t lda2, int K2,
               const float* B2, int64_t ldb2, const float* bias, int act, const float* aux, int64_t ldaux, float* C,
-              int64_t ldc, int M, int N, int mode, gts_stream_t st, const float* bias2 = nullptr) {
+              int64_t ldc, int M, int N, int mode, gts_stream_t st, const float* bias2 = nullptr,
+              uint32_t* relu_bits_out = nullptr, const uint32_t* aux_bits = nullptr) {
   gts_gemm_nt_args a;
   a.scatter_idx = nullptr; a.ld_idx = 0; a.scatter_out = nullptr; a.ld_out = 0;
+  a.relu_bits_out = relu_bits_out; a.ld_bits_out = N / 32; a.aux_bits = aux_bits; a.ld_aux_bits = N / 32;
   a.bias2 = bias2;
   a.A1 = A1; a.lda1 = lda1; a.K1 = K1; a.A2 = A2; a.lda2 = lda2; a.K2 = K2;
   a.B1 = B1; a.ldb1 = ldb1; a.B2 = B2; a.ldb2 = ldb2; a.bias = bias; a.aux = aux; a.ldaux = ldaux;
@@ -127,7 +141,11 @@ int gts_sage_forward(const gts_sage_layer* layers, int32_t n_layers,
                ly.din, mode, stream));
     float* neigh = at(workspace, training ? pl.neigh[l] : pl.neigh[0]);
     int32_t* arg = training ? reinterpret_cast<int32_t*>(at(workspace, pl.arg[l])) : nullptr;
-    GTS_TRY(gts_segmax_fwd(P, ly.din, indptr, indices, N, ly.din, neigh, ly.din, arg, ly.din, stream));
+    if (training && pl.neigh_bits[l])
+      GTS_TRY(gts_segmax_fwd_bits(P, ly.din, indptr, indices, N, ly.din, neigh, ly.din, arg, ly.din,
+                                  reinterpret_cast<uint32_t*>(at(workspace, pl.neigh_bits[l])), ly.din / 32, stream));
+    else
+      GTS_TRY(gts_segmax_fwd(P, ly.din, indptr, indices, N, ly.din, neigh, ly.din, arg, ly.din, stream));
     const bool last = (l + 1 == n_layers);
     float* out;
     int64_t ldo;
@@ -135,7 +153,8 @@ int gts_sage_forward(const gts_sage_layer* layers, int32_t n_layers,
     else if (training) { out = at(workspace, pl.out[l]); ldo = ly.dout; }
     else { out = at(workspace, (l & 1) ? pl.g1 : pl.g0); ldo = ly.dout; }
     GTS_TRY(nt(h, ldh, ly.din, ly.Ws, ly.din, neigh, ly.din, ly.din, ly.Wn, ly.din, ly.b,
-               ly.relu ? GTS_ACT_RELU : GTS_ACT_NONE, nullptr, 0, out, ldo, N, ly.dout, mode, stream, ly.b2));
+               ly.relu ? GTS_ACT_RELU : GTS_ACT_NONE, nullptr, 0, out, ldo, N, ly.dout, mode, stream, ly.b2,
+               (training && pl.out_bits[l]) ? reinterpret_cast<uint32_t*>(at(workspace, pl.out_bits[l])) : nullptr));
     h = out; ldh = ldo;
   }
   return GTS_OK;
@@ -207,8 +226,13 @@ static int backward_range(const gts_sage_layer* layers, const gts_sage_layer_gra
     // epilogue (GTS_ACT_MASK_POS_SCATTER) is correct but slower — 320 us against 60 (GEMM) + 118 (zero-fill + scatter):
     // four epilogue warps per SM cannot keep as many REDs in flight as a full-occupancy scatter kernel.
     float* dNeigh = at(workspace, pl.P);
-    GTS_TRY(nt(dZ, ldz, ly.dout, WnT, ly.dout, nullptr, 0, 0, nullptr, 0, nullptr, GTS_ACT_MASK_POS, neigh, ly.din, dNeigh,
-               ly.din, N, ly.din, mode, stream));
+    if (pl.neigh_bits[l])      // the mask (neigh > 0) as bits: 1/32 of the float operand's traffic in the epilogue
+      GTS_TRY(nt(dZ, ldz, ly.dout, WnT, ly.dout, nullptr, 0, 0, nullptr, 0, nullptr, GTS_ACT_MASK_BITS, nullptr, 0, dNeigh,
+                 ly.din, N, ly.din, mode, stream, nullptr, nullptr,
+                 reinterpret_cast<const uint32_t*>(at(workspace, pl.neigh_bits[l]))));
+    else
+      GTS_TRY(nt(dZ, ldz, ly.dout, WnT, ly.dout, nullptr, 0, 0, nullptr, 0, nullptr, GTS_ACT_MASK_POS, neigh, ly.din, dNeigh,
+                 ly.din, N, ly.din, mode, stream));
     float* dP = at(workspace, pl.dP);
     if (csc_indptr && csc_indices)
       GTS_TRY(gts_segmax_bwd_det(dNeigh, ly.din, arg, ly.din, csc_indptr, csc_indices, N, ly.din, dP, ly.din, stream));
@@ -224,8 +248,13 @@ static int backward_range(const gts_sage_layer* layers, const gts_sage_layer_gra
       else { dh = at(workspace, ((n_layers - 1 - l) & 1) ? pl.g1 : pl.g0); lddh = ly.din; }
       // dh = (dZ Ws + dP' Wp) * (h > 0): h is the ReLU output of layer l-1 (no mask for the input features)
       const bool mask = l > 0 && layers[l - 1].relu != 0;
-      GTS_TRY(nt(dZ, ldz, ly.dout, WsT, ly.dout, dP, ly.din, ly.din, WpT, ly.din, nullptr,
-                 mask ? GTS_ACT_MASK_POS : GTS_ACT_NONE, mask ? h : nullptr, ldh, dh, lddh, N, ly.din, mode, stream));
+      if (mask && pl.out_bits[l - 1])
+        GTS_TRY(nt(dZ, ldz, ly.dout, WsT, ly.dout, dP, ly.din, ly.din, WpT, ly.din, nullptr, GTS_ACT_MASK_BITS, nullptr, 0,
+                   dh, lddh, N, ly.din, mode, stream, nullptr, nullptr,
+                   reinterpret_cast<const uint32_t*>(at(workspace, pl.out_bits[l - 1]))));
+      else
+        GTS_TRY(nt(dZ, ldz, ly.dout, WsT, ly.dout, dP, ly.din, ly.din, WpT, ly.din, nullptr,
+                   mask ? GTS_ACT_MASK_POS : GTS_ACT_NONE, mask ? h : nullptr, ldh, dh, lddh, N, ly.din, mode, stream));
     }
   }
   return GTS_OK;

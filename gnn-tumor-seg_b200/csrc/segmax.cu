@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
 segmax_fwd_pipe_kernel(const float* __restrict__ P, int64_t ldp, const int32_t* __restrict__ indptr,
                        const int32_t* __restrict__ indices, int32_t N,
                        float* __restrict__ neigh, int64_t ldn, int32_t* __restrict__ argmax, int64_t ldarg,
-                       int32_t steps, const FoldConst fc) {
+                       int32_t steps, const FoldConst fc, uint32_t* __restrict__ pos_bits, int64_t ld_bits) {
   constexpr int G = 2 * R;      // rows per loop iteration (two stages)
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -431,6 +431,19 @@ segmax_fwd_pipe_kernel(const float* __restrict__ P, int64_t ldp, const int32_t* 
       stg_na(reinterpret_cast<float4*>(neigh + (int64_t)v * ldn) + slab4 + lane + 32 * c, best[c]);
       if (WRITE_ARG) stg_na(reinterpret_cast<int4*>(argmax + (int64_t)v * ldarg) + slab4 + lane + 32 * c, arg[c]);
     }
+    if (pos_bits) {
+      // (neigh > 0) as bits in the layout of GTS_ACT_MASK_BITS: lanes 8q .. 8q+7 hold the 32 columns of word 4c + q
+      // (column 4 * (lane & 7) + comp <-> bit 8 * comp + (lane & 7)): byte q of each component's ballot
+      const int q = lane >> 3;
+      const uint32_t sel = (uint32_t)q | ((4u + (uint32_t)q) << 4);
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) {
+        const uint32_t b0 = __ballot_sync(full, best[c].x > 0.f), b1 = __ballot_sync(full, best[c].y > 0.f);
+        const uint32_t b2 = __ballot_sync(full, best[c].z > 0.f), b3 = __ballot_sync(full, best[c].w > 0.f);
+        const uint32_t w = __byte_perm(__byte_perm(b0, b1, sel), __byte_perm(b2, b3, sel), 0x5410);
+        if ((lane & 7) == 0) pos_bits[(int64_t)v * ld_bits + (slab4 >> 3) + 4 * c + q] = w;
+      }
+    }
     v = v1;
     beg = nbeg; end = nend; my_idx = n_idx;
   }
@@ -440,7 +453,7 @@ segmax_fwd_pipe_kernel(const float* __restrict__ P, int64_t ldp, const int32_t* 
 template <int VEC, int kWarps, int FV, int R>
 static int launch_fwd_pipe(const float* P, int64_t ldp, const int32_t* indptr, const int32_t* indices, int32_t N,
                            float* neigh, int64_t ldn, int32_t* argmax, int64_t ldarg, cudaStream_t st, int piece_req,
-                           int slabs = 1) {
+                           int slabs = 1, uint32_t* pos_bits = nullptr, int64_t ld_bits = 0) {
   // piece_req = target nodes per piece (0: one contiguous range per CTA)
   const int64_t grid = std::min<int64_t>(sm_count(), ceil_div<int64_t>(N, kWarps));
   int64_t steps = 1;
@@ -455,9 +468,9 @@ static int launch_fwd_pipe(const float* P, int64_t ldp, const int32_t* indptr, c
   }();
   (void)max_l1;
   if (argmax)
-    segmax_fwd_pipe_kernel<VEC, true, kWarps, FV, R><<<dim3((unsigned)grid, slabs), kWarps * 32, 0, st>>>(P, ldp, indptr, indices, N, neigh, ldn, argmax, ldarg, (int32_t)steps, fold_const());
+    segmax_fwd_pipe_kernel<VEC, true, kWarps, FV, R><<<dim3((unsigned)grid, slabs), kWarps * 32, 0, st>>>(P, ldp, indptr, indices, N, neigh, ldn, argmax, ldarg, (int32_t)steps, fold_const(), pos_bits, ld_bits);
   else
-    segmax_fwd_pipe_kernel<VEC, false, kWarps, FV, R><<<dim3((unsigned)grid, slabs), kWarps * 32, 0, st>>>(P, ldp, indptr, indices, N, neigh, ldn, nullptr, 0, (int32_t)steps, fold_const());
+    segmax_fwd_pipe_kernel<VEC, false, kWarps, FV, R><<<dim3((unsigned)grid, slabs), kWarps * 32, 0, st>>>(P, ldp, indptr, indices, N, neigh, ldn, nullptr, 0, (int32_t)steps, fold_const(), pos_bits, ld_bits);
   GTS_LAUNCH_CHECK();
   return GTS_OK;
 }
@@ -848,6 +861,29 @@ int gts_segmax_fwd(const float* P, int64_t ldp, const int32_t* indptr, const int
   segmax_fwd_scalar_kernel<<<seg_grid(n_nodes), kSegThreads, 0, st>>>(P, ldp, indptr, indices, n_nodes, D, neigh, ldn, argmax, ldarg);
   GTS_LAUNCH_CHECK();
   return GTS_OK;
+}
+
+int gts_segmax_fwd_bits_supported(int32_t n_nodes, int32_t D, int64_t ldp) {
+  // the default software-pipelined D = 256 kernel (no A/B environment overrides of its configuration)
+  static const bool plain = !getenv("GTS_SEGMAX_GENERIC") && !getenv("GTS_SEGMAX_PIPE") && !getenv("GTS_SEGMAX_FOLD") &&
+                            !getenv("GTS_SEGMAX_STAGE") && !getenv("GTS_SEGMAX_SLABS");
+  return plain && D == 256 && ldp % 4 == 0 && n_nodes > 0 && (int64_t)n_nodes * ldp * 4 < ((int64_t)1 << 32);
+}
+
+int gts_segmax_fwd_bits(const float* P, int64_t ldp, const int32_t* indptr, const int32_t* indices,
+                        int32_t n_nodes, int32_t D, float* neigh, int64_t ldn,
+                        int32_t* argmax, int64_t ldarg, uint32_t* pos_bits, int64_t ld_bits, gts_stream_t stream) {
+  GTS_CHECK_ARG(n_nodes >= 0 && D >= 0, "gts_segmax_fwd_bits: negative size");
+  if (n_nodes == 0 || D == 0) return GTS_OK;
+  GTS_CHECK_ARG(P && indptr && neigh && pos_bits, "gts_segmax_fwd_bits: null pointer");
+  GTS_CHECK_ARG(ldp >= D && ldn >= D && (!argmax || ldarg >= D) && ld_bits >= D / 32, "gts_segmax_fwd_bits: leading dimension too small");
+  const bool vec_ok = (ldn % 4 == 0) && (!argmax || ldarg % 4 == 0) && aligned16(P) && aligned16(neigh) && (!argmax || aligned16(argmax));
+  if (!gts_segmax_fwd_bits_supported(n_nodes, D, ldp) || !vec_ok) {
+    set_error("gts_segmax_fwd_bits: D = %d / this layout is not supported (gts_segmax_fwd_bits_supported)", D);
+    return GTS_ERR_UNSUPPORTED;
+  }
+  return launch_fwd_pipe<2, 32, 3, 1>(P, ldp, indptr, indices, n_nodes, neigh, ldn, argmax, ldarg, as_stream(stream), 64, 1,
+                                      pos_bits, ld_bits);
 }
 
 int gts_segmax_bwd(const float* dNeigh, int64_t ldd, const int32_t* argmax, int64_t ldarg,

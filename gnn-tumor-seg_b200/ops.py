@@ -13,7 +13,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import ACT_MASK_POS, ACT_MASK_POS_SCATTER, ACT_NONE, ACT_RELU, GEMM_MODES, GemmNtArgs, check, ptr, require_cuda, stream_ptr
+from ._lib import ACT_MASK_BITS, ACT_MASK_POS, ACT_MASK_POS_SCATTER, ACT_NONE, ACT_RELU, GEMM_MODES, GemmNtArgs, check, ptr, require_cuda, stream_ptr
 
 # ---------------------------------------------------------------------------
 # arithmetic mode of the dense contractions (stated per run in bench/tests)
@@ -140,8 +140,11 @@ def edge_perm_compose(eid_csr, eid_csc):
 # ---------------------------------------------------------------------------
 # dense contractions
 # ---------------------------------------------------------------------------
-def gemm_nt(A1, B1, A2=None, B2=None, bias=None, act=ACT_NONE, aux=None, mode=None, out=None, bias2=None):
-    """act(A1 @ B1.T + A2 @ B2.T + bias); B* in nn.Linear layout [out,in]."""
+def gemm_nt(A1, B1, A2=None, B2=None, bias=None, act=ACT_NONE, aux=None, mode=None, out=None, bias2=None,
+            relu_bits_out=None, aux_bits=None):
+    """act(A1 @ B1.T + A2 @ B2.T + bias); B* in nn.Linear layout [out,in].
+    relu_bits_out (int32 [M, N/32], with ACT_RELU): receives the bit matrix of (C > 0); aux_bits (with ACT_MASK_BITS): the
+    mask as such a bit matrix (layout: include/gts.h GTS_ACT_MASK_BITS) — 256-wide tensor-core path only."""
     require_cuda(A1, B1, A2, B2, bias, aux)
     lib = _lib.load()
     A1 = _row_major_2d(A1)
@@ -177,6 +180,14 @@ def gemm_nt(A1, B1, A2=None, B2=None, bias=None, act=ACT_NONE, aux=None, mode=No
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=A1.device)
     a.C, a.ldc = ptr(out), _ld(out)
+    if relu_bits_out is not None:
+        require_cuda(relu_bits_out)
+        assert relu_bits_out.dtype == torch.int32 and tuple(relu_bits_out.shape) == (M, N // 32) and relu_bits_out.is_contiguous()
+        a.relu_bits_out, a.ld_bits_out = ptr(relu_bits_out), N // 32
+    if aux_bits is not None:
+        require_cuda(aux_bits)
+        assert aux_bits.dtype == torch.int32 and tuple(aux_bits.shape) == (M, N // 32) and aux_bits.is_contiguous()
+        a.aux_bits, a.ld_aux_bits = ptr(aux_bits), N // 32
     a.M, a.N, a.act = M, N, act
     a.mode = _gemm_mode if mode is None else (GEMM_MODES[mode] if isinstance(mode, str) else mode)
     check(lib.gts_gemm_nt(C.byref(a), stream_ptr()), "gts_gemm_nt")

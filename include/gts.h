@@ -49,6 +49,11 @@ enum gts_act {
   GTS_ACT_NONE = 0,
   GTS_ACT_RELU = 1,     /* C = max(acc + bias, 0) */
   GTS_ACT_MASK_POS = 2, /* C = (aux > 0) ? acc + bias : 0   (ReLU backward mask) */
+  GTS_ACT_MASK_BITS = 4,        /* as GTS_ACT_MASK_POS with the mask handed over as a BIT matrix (aux_bits, 1 bit per element
+                                 * instead of a 4-byte float: the ReLU mask of a 92 MB activation is 2.9 MB).  Word (m, n / 32),
+                                 * bit b  <->  column 32 * (n / 32) + 4 * (b & 7) + (b >> 3); written by gts_gemm_nt
+                                 * (relu_bits_out) and gts_segmax_fwd_bits.  CTA-pair tensor-core path only
+                                 * (gts_gemm_nt_bits_supported). */
   GTS_ACT_MASK_POS_SCATTER = 3  /* v = (aux > 0) ? acc : 0 is NOT stored to C: it is routed through saved arg-max indices,
                                  * scatter_out[scatter_idx[m,n], n] += v (fp32 RED; rows with idx < 0 and v == 0 skipped).
                                  * The backward of the neighbour max fused into the GEMM that produces its input:
@@ -120,9 +125,14 @@ typedef struct gts_gemm_nt_args {
   const float* bias2;   /* optional second bias vector, added to bias (DGL<=0.7 keeps fc_self.bias and fc_neigh.bias) */
   const int32_t* scatter_idx; int64_t ld_idx;   /* GTS_ACT_MASK_POS_SCATTER: arg-max indices [M,N] */
   float* scatter_out; int64_t ld_out;           /* GTS_ACT_MASK_POS_SCATTER: destination [rows,N], zero-filled */
+  uint32_t* relu_bits_out; int64_t ld_bits_out; /* optional with GTS_ACT_RELU: bit matrix [M, ld_bits_out words] of (C > 0) */
+  const uint32_t* aux_bits; int64_t ld_aux_bits; /* GTS_ACT_MASK_BITS: the mask, [M, ld_aux_bits words] */
 } gts_gemm_nt_args;
 
 GTS_API int gts_gemm_nt(const gts_gemm_nt_args* args, gts_stream_t stream);
+/* 1 when gts_gemm_nt honours relu_bits_out / GTS_ACT_MASK_BITS for this shape and mode (the 256-wide CTA-pair kernel:
+ * 3xTF32, M >= 256, N a multiple of 256); callers fall back to the float mask otherwise. */
+GTS_API int gts_gemm_nt_bits_supported(int32_t M, int32_t N, int32_t mode);
 
 /* Weight gradient: C[Mo,No] = A[K,Mo]^T * B[K,No]  (K = number of nodes).
  * Split-K over the grid with a deterministic second-pass reduction. */
@@ -171,6 +181,14 @@ GTS_API int gts_transpose(const float* in, int64_t ldin, int32_t rows, int32_t c
 GTS_API int gts_segmax_fwd(const float* P, int64_t ldp, const int32_t* indptr, const int32_t* indices,
                    int32_t n_nodes, int32_t D, float* neigh, int64_t ldn,
                    int32_t* argmax, int64_t ldarg, gts_stream_t stream);
+
+/* gts_segmax_fwd that also writes pos_bits = the bit matrix of (neigh > 0) in the layout of GTS_ACT_MASK_BITS
+ * ([n_nodes, ld_bits words]): the ReLU mask of fc_pool at the selected entries, consumed by the backward's dNeigh GEMM.
+ * D = 256 only (gts_segmax_fwd_bits_supported); returns GTS_ERR_UNSUPPORTED otherwise. */
+GTS_API int gts_segmax_fwd_bits_supported(int32_t n_nodes, int32_t D, int64_t ldp);
+GTS_API int gts_segmax_fwd_bits(const float* P, int64_t ldp, const int32_t* indptr, const int32_t* indices,
+                        int32_t n_nodes, int32_t D, float* neigh, int64_t ldn,
+                        int32_t* argmax, int64_t ldarg, uint32_t* pos_bits, int64_t ld_bits, gts_stream_t stream);
 
 /* dP[argmax[v,k], k] += dNeigh[v,k]; dP ([n_src_rows, D], leading dim lddp) is
  * zero-filled by the call.  fp32 atomics (order not deterministic). */
