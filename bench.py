@@ -470,6 +470,23 @@ def run_ours(args):
         ops.weighted_cross_entropy(net(bg, f), l, class_w).backward()
 
     breakdown = kernel_breakdown(autograd_step, ops)
+    if args.model == "sage":
+        # the PRODUCT path's own breakdown (gts_sage_step brackets its launch groups with CUDA events when asked): the
+        # per-op autograd path above runs the same kernels but with float ReLU masks instead of the bit matrices
+        import ctypes
+        lib = _lib.load()
+        step(0); torch.cuda.synchronize()
+        lib.gts_sage_profile(1)
+        step(0); torch.cuda.synchronize()
+        ms_k = (ctypes.c_float * 7)()
+        n_k = (ctypes.c_int32 * 7)()
+        _lib.check(lib.gts_sage_profile_read(ms_k, n_k, 7), "gts_sage_profile_read")
+        lib.gts_sage_profile(0)
+        names_k = ["gemm_nt", "segmax_fwd", "segmax_bwd", "gemm_tn2_colsum", "gemm_tn_colsum", "transpose", "ce_weighted"]
+        prod = {nm: {"ms": float(ms_k[i]), "calls": int(n_k[i])} for i, nm in enumerate(names_k) if n_k[i]}
+        if prod:
+            per_op_path = breakdown
+            breakdown = prod
     opt = trainer.optimizer if args.model == "sage" else gat_opt
     for p_ in net.parameters():
         if p_.grad is None:

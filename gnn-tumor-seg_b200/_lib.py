@@ -120,6 +120,8 @@ _SIGNATURES = {
                                           C.c_int64, C.c_void_p, C.c_size_t, C.c_int32, c_stream]),
     "gts_sage_step": (C.c_int, [C.POINTER(SageStepArgs), c_stream]),
     "gts_sage_step_backward_rest": (C.c_int, [C.POINTER(SageStepArgs), C.c_int32, C.c_int32, c_stream]),
+    "gts_sage_profile": (C.c_int, [C.c_int32]),
+    "gts_sage_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int32]),
     "gts_ce_weighted": (C.c_int, [c_f32p, C.c_int64, c_i64p, c_f32p, C.c_int32, C.c_int32, c_f32p, c_f32p,
                                   C.c_int64, c_stream]),
     "gts_scale_by_inv": (C.c_int, [c_f32p, C.c_int64, C.c_float, c_f32p, c_stream]),

@@ -4,6 +4,7 @@
 // stream, all scratch is carved from the caller's workspace.
 #include "common.cuh"
 #include <cstdlib>
+#include <vector>
 
 namespace gts {
 
@@ -80,6 +81,35 @@ static bool make_plan(const gts_sage_layer* layers, int L, int64_t N, bool train
   return true;
 }
 
+// Optional per-class device timing of the whole-stack calls (bench.py's step breakdown of the PRODUCT path): when
+// enabled, every launch group below is bracketed by two CUDA events on the caller's stream.  Off by default; never
+// enable it around a CUDA-graph capture.
+enum ProfKind { kProfGemmNt = 0, kProfSegFwd, kProfSegBwd, kProfTn2, kProfTn, kProfTranspose, kProfCe, kProfKinds };
+struct ProfState {
+  bool on = false;
+  struct Rec { int kind; cudaEvent_t e0, e1; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+static ProfState g_prof;
+struct Prof {
+  cudaStream_t st; int idx = -1;
+  Prof(int kind, gts_stream_t stream) : st(as_stream(stream)) {
+    if (!g_prof.on) return;
+    ProfState::Rec r{kind, g_prof.get(), g_prof.get()};
+    cudaEventRecord(r.e0, st);
+    g_prof.recs.push_back(r);
+    idx = (int)g_prof.recs.size() - 1;
+  }
+  ~Prof() { if (idx >= 0) cudaEventRecord(g_prof.recs[idx].e1, st); }
+};
+
 static inline float* at(void* ws, size_t off) { return reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + off); }
 
 #define GTS_TRY(expr)            \
@@ -99,6 +129,7 @@ static int nt(const float* A1, int64_t lda1, int K1, const float* B1, int64_t ld
   a.A1 = A1; a.lda1 = lda1; a.K1 = K1; a.A2 = A2; a.lda2 = lda2; a.K2 = K2;
   a.B1 = B1; a.ldb1 = ldb1; a.B2 = B2; a.ldb2 = ldb2; a.bias = bias; a.aux = aux; a.ldaux = ldaux;
   a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.act = act; a.mode = mode;
+  Prof prof(kProfGemmNt, st);
   return gts_gemm_nt(&a, st);
 }
 
@@ -141,11 +172,14 @@ int gts_sage_forward(const gts_sage_layer* layers, int32_t n_layers,
                ly.din, mode, stream));
     float* neigh = at(workspace, training ? pl.neigh[l] : pl.neigh[0]);
     int32_t* arg = training ? reinterpret_cast<int32_t*>(at(workspace, pl.arg[l])) : nullptr;
-    if (training && pl.neigh_bits[l])
-      GTS_TRY(gts_segmax_fwd_bits(P, ly.din, indptr, indices, N, ly.din, neigh, ly.din, arg, ly.din,
-                                  reinterpret_cast<uint32_t*>(at(workspace, pl.neigh_bits[l])), ly.din / 32, stream));
-    else
-      GTS_TRY(gts_segmax_fwd(P, ly.din, indptr, indices, N, ly.din, neigh, ly.din, arg, ly.din, stream));
+    {
+      Prof prof(kProfSegFwd, stream);
+      if (training && pl.neigh_bits[l])
+        GTS_TRY(gts_segmax_fwd_bits(P, ly.din, indptr, indices, N, ly.din, neigh, ly.din, arg, ly.din,
+                                    reinterpret_cast<uint32_t*>(at(workspace, pl.neigh_bits[l])), ly.din / 32, stream));
+      else
+        GTS_TRY(gts_segmax_fwd(P, ly.din, indptr, indices, N, ly.din, neigh, ly.din, arg, ly.din, stream));
+    }
     const bool last = (l + 1 == n_layers);
     float* out;
     int64_t ldo;
@@ -200,6 +234,7 @@ static int backward_range(const gts_sage_layer* layers, const gts_sage_layer_gra
         GTS_TRY(push(ly.Wp, ly.din, ly.din, pl.wpT[l]));
       }
     }
+    Prof prof(kProfTranspose, stream);
     if (tb.n > 0) GTS_TRY(launch_transpose_batch(tb, as_stream(stream)));
   }
   for (int l = layer_hi - 1; l >= layer_lo; --l) {
@@ -216,8 +251,11 @@ static int backward_range(const gts_sage_layer* layers, const gts_sage_layer_gra
     void* gws = at(workspace, pl.gemm_ws);
     // (dZ already carries this layer's ReLU mask: the consumer's epilogue applied (out > 0))
     // dWs = dZ^T h, dWn = dZ^T neigh and db = column sums of dZ: one pass over dZ in the 3xTF32 mode
-    GTS_TRY(gts_gemm_tn2_colsum(dZ, ldz, h, ldh, neigh, ly.din, g.dWs, g.dWn, ly.din, ly.dout, ly.din, N, mode, g.db, gws,
-                                pl.gemm_ws_bytes, stream));
+    {
+      Prof prof(kProfTn2, stream);
+      GTS_TRY(gts_gemm_tn2_colsum(dZ, ldz, h, ldh, neigh, ly.din, g.dWs, g.dWn, ly.din, ly.dout, ly.din, N, mode, g.db, gws,
+                                  pl.gemm_ws_bytes, stream));
+    }
     if (g.db2 && N > 0)      // fc_neigh.bias enters the output as fc_self.bias does: same gradient, its own arena slot
       GTS_CUDA(cudaMemcpyAsync(g.db2, g.db, sizeof(float) * (size_t)ly.dout, cudaMemcpyDeviceToDevice, as_stream(stream)));
     // dNeigh' = (dZ Wn) * (neigh > 0)
@@ -234,11 +272,17 @@ static int backward_range(const gts_sage_layer* layers, const gts_sage_layer_gra
       GTS_TRY(nt(dZ, ldz, ly.dout, WnT, ly.dout, nullptr, 0, 0, nullptr, 0, nullptr, GTS_ACT_MASK_POS, neigh, ly.din, dNeigh,
                  ly.din, N, ly.din, mode, stream));
     float* dP = at(workspace, pl.dP);
-    if (csc_indptr && csc_indices)
-      GTS_TRY(gts_segmax_bwd_det(dNeigh, ly.din, arg, ly.din, csc_indptr, csc_indices, N, ly.din, dP, ly.din, stream));
-    else
-      GTS_TRY(gts_segmax_bwd(dNeigh, ly.din, arg, ly.din, N, ly.din, dP, ly.din, N, stream));
-    GTS_TRY(gts_gemm_tn_colsum(dP, ly.din, h, ldh, g.dWp, ly.din, ly.din, ly.din, N, mode, g.dbp, gws, pl.gemm_ws_bytes, stream));
+    {
+      Prof prof(kProfSegBwd, stream);
+      if (csc_indptr && csc_indices)
+        GTS_TRY(gts_segmax_bwd_det(dNeigh, ly.din, arg, ly.din, csc_indptr, csc_indices, N, ly.din, dP, ly.din, stream));
+      else
+        GTS_TRY(gts_segmax_bwd(dNeigh, ly.din, arg, ly.din, N, ly.din, dP, ly.din, N, stream));
+    }
+    {
+      Prof prof(kProfTn, stream);
+      GTS_TRY(gts_gemm_tn_colsum(dP, ly.din, h, ldh, g.dWp, ly.din, ly.din, ly.din, N, mode, g.dbp, gws, pl.gemm_ws_bytes, stream));
+    }
     if (l > 0 || dfeats) {
       const float* WsT = at(workspace, pl.wsT[l]);
       const float* WpT = at(workspace, pl.wpT[l]);
@@ -294,12 +338,35 @@ int gts_sage_step(const gts_sage_step_args* a, gts_stream_t stream) {
   float* dlogits = at(a->workspace, pl.dlogits);
   GTS_TRY(gts_sage_forward(a->layers, a->n_layers, a->indptr, a->indices, a->n_nodes, a->feats, a->ldf, a->logits, a->ldl,
                            a->workspace, a->workspace_bytes, 1, a->mode, stream));
-  GTS_CUDA(cudaMemsetAsync(a->sums, 0, 2 * sizeof(float), as_stream(stream)));
-  GTS_TRY(gts_ce_weighted(a->logits, a->ldl, a->labels, a->class_w, a->n_nodes, C, a->sums, dlogits, C, stream));
-  if (a->normalize)      // gradients of the weighted MEAN (model/gnn_model.py:30,42): d/dz of sum(w nll) / sum(w)
-    GTS_TRY(gts_scale_by_inv(dlogits, (int64_t)a->n_nodes * C, 1.0f, a->sums + 1, stream));
+  {
+    Prof prof(kProfCe, stream);
+    GTS_CUDA(cudaMemsetAsync(a->sums, 0, 2 * sizeof(float), as_stream(stream)));
+    GTS_TRY(gts_ce_weighted(a->logits, a->ldl, a->labels, a->class_w, a->n_nodes, C, a->sums, dlogits, C, stream));
+    if (a->normalize)      // gradients of the weighted MEAN (model/gnn_model.py:30,42): d/dz of sum(w nll) / sum(w)
+      GTS_TRY(gts_scale_by_inv(dlogits, (int64_t)a->n_nodes * C, 1.0f, a->sums + 1, stream));
+  }
   return backward_range(a->layers, a->grads, a->n_layers, a->n_layers, a->bwd_layer_lo, a->csc_indptr, a->csc_indices,
                         a->n_nodes, a->feats, a->ldf, dlogits, C, nullptr, 0, a->workspace, a->workspace_bytes, a->mode, stream);
+}
+
+int gts_sage_profile(int32_t enable) {
+  for (auto& r : g_prof.recs) { g_prof.pool.push_back(r.e0); g_prof.pool.push_back(r.e1); }
+  g_prof.recs.clear();
+  g_prof.on = enable != 0;
+  return GTS_OK;
+}
+
+int gts_sage_profile_read(float* ms_by_kind, int32_t* calls_by_kind, int32_t n_kinds) {
+  GTS_CHECK_ARG(ms_by_kind && calls_by_kind && n_kinds >= kProfKinds, "gts_sage_profile_read: need %d slots", (int)kProfKinds);
+  for (int k = 0; k < n_kinds; ++k) { ms_by_kind[k] = 0.f; calls_by_kind[k] = 0; }
+  for (auto& r : g_prof.recs) {
+    GTS_CUDA(cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    GTS_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    ms_by_kind[r.kind] += ms;
+    calls_by_kind[r.kind] += 1;
+  }
+  return GTS_OK;
 }
 
 int gts_sage_step_backward_rest(const gts_sage_step_args* a, int32_t layer_hi, int32_t layer_lo, gts_stream_t stream) {

@@ -295,6 +295,14 @@ GTS_API int gts_sage_step(const gts_sage_step_args* args, gts_stream_t stream);
 /* Backward layers layer_hi-1 .. layer_lo of a step started with bwd_layer_lo = layer_hi. */
 GTS_API int gts_sage_step_backward_rest(const gts_sage_step_args* args, int32_t layer_hi, int32_t layer_lo, gts_stream_t stream);
 
+/* Per-class device timing of the whole-stack entry points above (bench.py's step breakdown of the product path):
+ * gts_sage_profile(1) brackets every launch group of the following gts_sage_forward / _backward / _step calls with CUDA
+ * events; gts_sage_profile_read sums them per class — 0 gemm_nt, 1 segmax_fwd, 2 segmax_bwd, 3 gemm_tn2_colsum,
+ * 4 gemm_tn_colsum, 5 transpose, 6 ce_weighted (7 slots) — after synchronising on the events; gts_sage_profile(0) stops
+ * and discards.  A measurement aid: not thread-safe, never enable it around a CUDA-graph capture. */
+GTS_API int gts_sage_profile(int32_t enable);
+GTS_API int gts_sage_profile_read(float* ms_by_kind, int32_t* calls_by_kind, int32_t n_kinds);
+
 /* ------------------------------------------------------------------------
  * K8 — weighted-mean cross entropy (model/gnn_model.py:30,42).
  * ------------------------------------------------------------------------ */
