@@ -164,6 +164,26 @@ def synth_batches(batch, n_batches, rank):
     return out
 
 
+def gat_flops(n_nodes):
+    """Algorithmic fwd+bwd flops of the GAT benchmark config: fc GEMMs 20 -> 4x256, 3 x (1024 -> 4x256; the
+    residual of layer 2 is the identity), 1024 -> 1x4; fwd+bwd ~ 3x fwd (98 % of the model's flops are these GEMMs)."""
+    hf = GAT_LAYER_SIZES[0] * GAT_HEADS[0]
+    fwd = 2 * n_nodes * (IN_FEATS * hf + (len(GAT_LAYER_SIZES) - 1) * hf * hf + hf * N_CLASSES)
+    return 3 * fwd
+
+
+def gat_edge_bytes(n_nodes, n_edges):
+    """Algorithmic bytes of the three fused edge kernels summed over the 5 GATConv layers."""
+    cfg = [(h, f) for f, h in zip(GAT_LAYER_SIZES, GAT_HEADS)] + [(1, N_CLASSES)]
+    out = {"gts_gat_fwd": 0, "gts_gat_bwd_dst": 0, "gts_gat_bwd_src": 0}
+    for H, F in cfg:
+        nhf, nh = n_nodes * H * F, n_nodes * H
+        out["gts_gat_fwd"] += 4 * (2 * nhf + 4 * nh) + 4 * (n_nodes + 1 + n_edges)
+        out["gts_gat_bwd_dst"] += 4 * (2 * nhf + 5 * nh + n_edges * H) + 4 * (n_nodes + 1 + n_edges)
+        out["gts_gat_bwd_src"] += 4 * (2 * nhf + n_edges * H + 6 * nh) + 4 * (n_nodes + 1 + 2 * n_edges)
+    return out
+
+
 def model_flops_bytes(n_nodes, n_edges):
     """Algorithmic fwd+bwd flops of the 7x256 stack: fwd = sum over layers of
     2*N*Din^2 (fc_pool) + 2*N*2Din*Dout (concat GEMM); fwd+bwd ~ 3x."""
@@ -254,6 +274,11 @@ def kernel_breakdown(step_fn, ops):
              "scale_by_inv_"]
     orig = {n: getattr(ops, n) for n in names}
     records = []
+    # the GAT edge kernels are called on the library object itself (ops.GatLayerFn): wrap them there
+    from gnn_tumor_seg_b200 import _lib as _l
+    lib = _l.load()
+    lib_names = ["gts_gat_scores", "gts_gat_fwd", "gts_gat_act_bwd", "gts_gat_bwd_dst", "gts_gat_bwd_src", "gts_gat_attn_grad2"]
+    lib_orig = {n: getattr(lib, n) for n in lib_names}
 
     def wrap(n):
         f = orig[n]
@@ -274,12 +299,28 @@ def kernel_breakdown(step_fn, ops):
         torch.cuda.synchronize()
         for n in names:
             setattr(ops, n, wrap(n))
+
+        def wrap_lib(n):
+            f = lib_orig[n]
+
+            def g(*a):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = f(*a)
+                e1.record()
+                records.append((n, e0, e1))
+                return r
+            return g
+        for n in lib_names:
+            setattr(lib, n, wrap_lib(n))
         step_fn()
         torch.cuda.synchronize()
     finally:
         ops.set_stack_path(stack)
         for n in names:
             setattr(ops, n, orig[n])
+        for n in lib_names:
+            setattr(lib, n, lib_orig[n])
     out = {}
     for n, e0, e1 in records:
         d = out.setdefault(n, {"ms": 0.0, "calls": 0})
@@ -508,7 +549,9 @@ def run_ours(args):
     gemm_flops = 2.0 * n_nodes * 2 * D * D
     gemm_tflops = gemm_flops / (ms_gemm * 1e-3) / 1e12
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
-    passes = {"fp32": 1, "tf32": 1, "tf32x3": 3}[args.mode]
+    # executed tensor work per algorithmic flop: tf32x3 = hi*hi in TF32 + two bf16 cross terms at twice the rate = 2
+    # TF32-equivalents (NT and, since round 2, TN kernels alike)
+    passes = {"fp32": 1, "tf32": 1, "tf32x3": 2}[args.mode]
     kern = {
         "segmax_fwd": {"ms": ms_seg, "bound": "hbm", "achieved": seg_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                        "frac": seg_gbs / peaks["hbm_gbs"], "alg_bytes": seg_bytes},
@@ -530,22 +573,36 @@ def run_ours(args):
                 kern["gemm_concat_k512"]["ncu"] = {"tensor_pipe_pct_of_elapsed": d_["tensor_pipe_pct_of_elapsed"],
                                                    "sm_clock_ghz": d_.get("sm_clock_ghz"), "dram_pct": d_.get("dram_pct"),
                                                    "lts_pct": d_.get("lts_pct"), "duration_us": d_.get("duration_us")}
+    if args.model == "gat":
+        # the fused edge kernels against the measured HBM roofline, on the algorithmic bytes of SURVEY.md §8d (K5)
+        for nm, byt in gat_edge_bytes(n_nodes, n_edges).items():
+            if nm in breakdown and breakdown[nm]["ms"] > 0:
+                gbs_ = byt / (breakdown[nm]["ms"] * 1e-3) / 1e9
+                kern[nm[4:]] = {"ms": breakdown[nm]["ms"], "calls": breakdown[nm]["calls"], "bound": "hbm", "achieved": gbs_,
+                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs_ / peaks["hbm_gbs"], "alg_bytes": byt,
+                                "traffic": traffic_of(ncu, nm[4:] + "_kernel"),
+                                "note": "all 5 layers' launches of this kernel; gathers of 1 KB head slices come from L1/L2"}
     tot = sum(v["ms"] for v in breakdown.values()) or 1.0
     share = {k: {"ms": round(v["ms"], 4), "calls": v["calls"], "share": round(v["ms"] / tot, 4)}
              for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])}
     dominant = next(iter(share))
     if dominant in ("gemm_nt", "gemm_tn", "gemm_tn_colsum", "gemm_tn2_colsum"):
         gemm_ms = sum(breakdown.get(k, {"ms": 0})["ms"] for k in ("gemm_nt", "gemm_tn", "gemm_tn_colsum", "gemm_tn2_colsum"))
-        flops = model_flops_bytes(n_nodes, n_edges)
+        flops = model_flops_bytes(n_nodes, n_edges) if args.model == "sage" else gat_flops(n_nodes)
         ach = flops / (gemm_ms * 1e-3) / 1e12
         roofline = {"kernel": "gemm (tcgen05 tf32)" if args.mode != "fp32" else "gemm (simt fp32)", "bound": "tensor",
                     "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
                     "traffic": kern["gemm_concat_k512"]["traffic"],
                     "executed_tflops": ach * passes,
                     "note": "algorithmic fwd+bwd flops of the step / summed GEMM launch time in the step (the tf32x3 mode "
-                            "executes 3 tensor-core products per algorithmic flop - hi*hi in TF32 plus two cross terms, bf16 MMAs "
-                            "in the NT kernels, TF32 in the TN kernels: see executed_tflops); traffic = DRAM bytes of "
-                            "one concat-GEMM launch (ncu); peak = 1/2 measured sustained bf16 (%s)" % peaks["src"]}
+                            "executes 2 TF32-equivalents of tensor work per algorithmic flop - hi*hi in TF32 plus two bf16 cross "
+                            "terms at twice the rate: see executed_tflops); traffic = DRAM bytes of one concat-GEMM launch "
+                            "(ncu); peak = 1/2 measured sustained bf16 (%s)" % peaks["src"]}
+    elif args.model == "gat" and dominant[4:] in kern:
+        k = kern[dominant[4:]]
+        roofline = {"kernel": dominant[4:], "bound": "hbm", "achieved": k["achieved"], "peak": k["peak"], "unit": "GB/s",
+                    "frac": k["frac"], "traffic": k.get("traffic"),
+                    "note": "algorithmic bytes of the fused GAT edge kernel over the 5 layers / its summed CUDA-event time; peak %s" % peaks["src"]}
     else:
         k = kern["segmax_fwd"]
         roofline = {"kernel": "segmax_fwd", "bound": "hbm", "achieved": k["achieved"], "peak": k["peak"],
