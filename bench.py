@@ -478,6 +478,7 @@ def run_ours(args):
         clocks = sampler2.stop()
         ms = g0_.elapsed_time(g1_) / args.steps
         loss_val = float(loss)
+        launches = args.steps * gsteps[0].launches_per_replay       # kernel nodes replayed inside this timed region
     e2e_steps(max(3, args.warmup // 2))
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -352,8 +352,10 @@ class GraphedStep:
         # warm-up on a side stream (lazy initialisation: function attributes, tensor-map entry point), then capture
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(dev))
+        n0 = ops.launch_counter["n"]
         with torch.cuda.stream(s):
             self._body(BatchedGraph)
+        self.launches_per_replay = ops.launch_counter["n"] - n0        # kernels one replay stands for
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
         if trainer.world_size == 1:
