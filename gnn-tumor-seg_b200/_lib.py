@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GTS_LIB_PATH") or os.path.join(_HERE, "libgts.so")     # override: A/B builds of the library
 
 GTS_OK = 0
-ACT_NONE, ACT_RELU, ACT_MASK_POS, ACT_MASK_POS_SCATTER, ACT_MASK_BITS = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_MASK_POS, ACT_MASK_POS_SCATTER, ACT_MASK_BITS, ACT_MASK_BITS_SCATTER = 0, 1, 2, 3, 4, 5
 GEMM_FP32, GEMM_TF32, GEMM_TF32X3 = 0, 1, 2
 GEMM_MODES = {"fp32": GEMM_FP32, "tf32": GEMM_TF32, "tf32x3": GEMM_TF32X3}
 

@@ -460,13 +460,15 @@ int gts_gemm_nt(const gts_gemm_nt_args* a, gts_stream_t stream) {
   GTS_CHECK_ARG(a != nullptr, "gts_gemm_nt: args is null");
   GTS_CHECK_ARG(a->M >= 0 && a->N >= 0 && a->K1 >= 0 && a->K2 >= 0, "gts_gemm_nt: negative size");
   if (a->M == 0 || a->N == 0) return GTS_OK;
-  GTS_CHECK_ARG(a->C != nullptr || a->act == GTS_ACT_MASK_POS_SCATTER, "gts_gemm_nt: C is null");
+  GTS_CHECK_ARG(a->C != nullptr || a->act == GTS_ACT_MASK_POS_SCATTER || a->act == GTS_ACT_MASK_BITS_SCATTER, "gts_gemm_nt: C is null");
   GTS_CHECK_ARG(a->act != GTS_ACT_MASK_POS_SCATTER || (a->scatter_idx && a->scatter_out && a->aux),
                 "gts_gemm_nt: GTS_ACT_MASK_POS_SCATTER needs aux, scatter_idx and scatter_out");
   GTS_CHECK_ARG(a->K1 == 0 || (a->A1 && a->B1), "gts_gemm_nt: A1/B1 null with K1 > 0");
-  GTS_CHECK_ARG(a->act >= GTS_ACT_NONE && a->act <= GTS_ACT_MASK_BITS, "gts_gemm_nt: unknown act %d", a->act);
+  GTS_CHECK_ARG(a->act >= GTS_ACT_NONE && a->act <= GTS_ACT_MASK_BITS_SCATTER, "gts_gemm_nt: unknown act %d", a->act);
+  GTS_CHECK_ARG(a->act != GTS_ACT_MASK_BITS_SCATTER || (a->scatter_idx && a->scatter_out && a->aux_bits),
+                "gts_gemm_nt: GTS_ACT_MASK_BITS_SCATTER needs aux_bits, scatter_idx and scatter_out");
   GTS_CHECK_ARG(a->act != GTS_ACT_MASK_POS || a->aux != nullptr, "gts_gemm_nt: GTS_ACT_MASK_POS needs aux");
-  const bool bits = a->act == GTS_ACT_MASK_BITS || a->relu_bits_out != nullptr;
+  const bool bits = a->act == GTS_ACT_MASK_BITS || a->act == GTS_ACT_MASK_BITS_SCATTER || a->relu_bits_out != nullptr;
   if (bits && !(gemm_nt_bits_supported(a->M, a->N, a->mode) && gemm_nt_tcgen05_supported(a))) {
     set_error("gts_gemm_nt: bit-matrix masks (GTS_ACT_MASK_BITS / relu_bits_out) are not supported for M=%d N=%d mode=%d "
               "(see gts_gemm_nt_bits_supported)", a->M, a->N, a->mode);

@@ -175,6 +175,9 @@ __device__ __forceinline__ float4 lds_128(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
 __device__ __forceinline__ float lds_32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
@@ -221,6 +224,8 @@ struct Params {
   float* colsum_partial;   // TN, A-in-TMEM kernel: [splits][M] column sums of the A operand (or null)
   uint32_t* bits_out; int64_t ld_bits_out;            // wide NT kernel: bit matrix of (C > 0) beside a ReLU output (or null)
   const uint32_t* aux_bits; int64_t ld_aux_bits;      // wide NT kernel, GTS_ACT_MASK_BITS: the mask as a bit matrix
+  const int32_t* scatter_idx; int64_t ld_idx;         // wide NT kernel, GTS_ACT_MASK_BITS_SCATTER: arg-max rows [M, N]
+  float* scatter_out; int64_t ld_out;                 //   and the zero-filled destination the masked tile is added into
   long long* trace;        // GTS_TRACE builds only: per-CTA clock64 records of gemm_x3ntw_kernel (tools/gemm_trace.py)
   int dbg;                 // GTS_TRACE builds only: ablation switches
 };
@@ -1463,6 +1468,16 @@ __device__ __forceinline__ void epilogue_half_regs(const Params& p, uint32_t t_b
     for (int j = 0; j < 8; ++j)
       mw[j] = j < jmax ? *reinterpret_cast<const uint4*>(brow + j * bstep4) : make_uint4(0u, 0u, 0u, 0u);
   }
+  // scatter form: the arg-max rows and the mask words of this lane's elements, fetched per chunk (one register set: with
+  // 128 accumulator registers live, a second set spilled)
+  int4 sidx[8];
+  uint32_t sw[8];
+  const int32_t* i_row = ACT == GTS_ACT_MASK_BITS_SCATTER ? p.scatter_idx + (int64_t)(m0 + rsub) * p.ld_idx + n0 + cc : nullptr;
+  const int istep4 = 4 * (int)p.ld_idx;
+  const uint32_t* sb_row = ACT == GTS_ACT_MASK_BITS_SCATTER ? p.aux_bits + (int64_t)(m0 + rsub) * p.ld_aux_bits + (n0 >> 5) : nullptr;
+  const int sbstep4 = 4 * (int)p.ld_aux_bits;
+  float* s_col = ACT == GTS_ACT_MASK_BITS_SCATTER ? p.scatter_out + n0 + cc : nullptr;      // column of this lane in the destination
+  const uint32_t s_ld_bytes = (uint32_t)(p.ld_out * 4);
   mbar_wait(full_bar, full_phase);
   tcgen05_fence_after();
   uint32_t v[4][32];
@@ -1481,6 +1496,13 @@ __device__ __forceinline__ void epilogue_half_regs(const Params& p, uint32_t t_b
       for (int j = 0; j < 8; ++j)
         if (j < jmax) aux[(c + 1) & 1][j] = ldg_nc_na(reinterpret_cast<const float4*>(a_row + j * step4 + 32 * (c + 1)));
     }
+    if (ACT == GTS_ACT_MASK_BITS_SCATTER) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sidx[j] = j < jmax ? __ldg(reinterpret_cast<const int4*>(i_row + j * istep4 + 32 * c)) : make_int4(-1, -1, -1, -1);
+        sw[j] = j < jmax ? __ldg(sb_row + j * sbstep4 + c) : 0u;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       sts_128(stg_w + 16 * j, v[c][4 * j], v[c][4 * j + 1], v[c][4 * j + 2], v[c][4 * j + 3]);
@@ -1492,11 +1514,26 @@ __device__ __forceinline__ void epilogue_half_regs(const Params& p, uint32_t t_b
         const float4 a = aux[c & 1][j];
         x.x = a.x > 0.f ? x.x : 0.f; x.y = a.y > 0.f ? x.y : 0.f;
         x.z = a.z > 0.f ? x.z : 0.f; x.w = a.w > 0.f ? x.w : 0.f;
-      } else if (ACT == GTS_ACT_MASK_BITS) {
+      } else if (ACT == GTS_ACT_MASK_BITS || ACT == GTS_ACT_MASK_BITS_SCATTER) {
         // bit 8 * comp + (lane & 7) of the chunk's word <-> column 4 * (lane & 7) + comp
-        const uint32_t w = (c == 0 ? mw[j].x : c == 1 ? mw[j].y : c == 2 ? mw[j].z : mw[j].w) >> (lane & 7);
+        const uint32_t w = (ACT == GTS_ACT_MASK_BITS_SCATTER ? sw[j]
+                                                             : (c == 0 ? mw[j].x : c == 1 ? mw[j].y : c == 2 ? mw[j].z : mw[j].w)) >> (lane & 7);
         x.x = (w & 0x1u) ? x.x : 0.f; x.y = (w & 0x100u) ? x.y : 0.f;
         x.z = (w & 0x10000u) ? x.z : 0.f; x.w = (w & 0x1000000u) ? x.w : 0.f;
+        if (ACT == GTS_ACT_MASK_BITS_SCATTER) {
+          // dP[arg[v,k], k] += x: the backward of the neighbour max, straight out of the GEMM that produces its input
+          // (zeros — half of the tile after the mask — and rows without an arg-max are skipped)
+          const int4 a = sidx[j];
+          auto dst = [&](int32_t u, int comp) {
+            uint64_t addr;
+            asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"((uint32_t)u), "r"(s_ld_bytes), "l"(s_col + 32 * c + comp));
+            return reinterpret_cast<float*>(addr);
+          };
+          if (x.x != 0.f && a.x >= 0) red_add_f32(dst(a.x, 0), x.x);
+          if (x.y != 0.f && a.y >= 0) red_add_f32(dst(a.y, 1), x.y);
+          if (x.z != 0.f && a.z >= 0) red_add_f32(dst(a.z, 2), x.z);
+          if (x.w != 0.f && a.w >= 0) red_add_f32(dst(a.w, 3), x.w);
+        }
       } else {
         x.x += b[c].x; x.y += b[c].y; x.z += b[c].z; x.w += b[c].w;
         if (ACT == GTS_ACT_RELU) {
@@ -1512,7 +1549,7 @@ __device__ __forceinline__ void epilogue_half_regs(const Params& p, uint32_t t_b
         const uint32_t w01 = __byte_perm(b0, b1, sel), w23 = __byte_perm(b2, b3, sel);
         if ((lane & 7) == 0 && j < jmax) bits_row[j * bits_step4 + c] = __byte_perm(w01, w23, 0x5410);
       }
-      if (j < jmax && !GTS_DBG(0)) *reinterpret_cast<float4*>(c_row + j * step4 + 32 * c) = x;
+      if (ACT != GTS_ACT_MASK_BITS_SCATTER && j < jmax && !GTS_DBG(0)) *reinterpret_cast<float4*>(c_row + j * step4 + 32 * c) = x;
     }
     __syncwarp();
   }
@@ -1913,6 +1950,7 @@ gemm_x3ntw_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
                                                tmem_empty_leader + acc * 8, rank == 0)
           if (p.act == GTS_ACT_MASK_POS) GTS_EPI(GTS_ACT_MASK_POS);
           else if (p.act == GTS_ACT_MASK_BITS) GTS_EPI(GTS_ACT_MASK_BITS);
+          else if (p.act == GTS_ACT_MASK_BITS_SCATTER) GTS_EPI(GTS_ACT_MASK_BITS_SCATTER);
           else if (p.act == GTS_ACT_RELU) GTS_EPI(GTS_ACT_RELU);
           else GTS_EPI(GTS_ACT_NONE);
 #undef GTS_EPI
@@ -2117,11 +2155,15 @@ bool gemm_nt_tcgen05_supported(const gts_gemm_nt_args* a) {
   const bool two = a->A2 && a->B2 && a->K2 > 0;
   if (two && (!tc::operand_ok(a->A2, a->lda2) || !tc::operand_ok(a->B2, a->ldb2))) return false;
   if (a->act == GTS_ACT_MASK_POS_SCATTER) return false;     // scatter epilogue: SIMT kernel only (measured slower when fused into the tcgen05 epilogue)
-  if (!tc::al16(a->C) || a->ldc % 4 != 0) return false;
+  if (a->act != GTS_ACT_MASK_BITS_SCATTER && (!tc::al16(a->C) || a->ldc % 4 != 0)) return false;
   if (a->bias && !tc::al16(a->bias)) return false;
   if (a->bias2 && !tc::al16(a->bias2)) return false;
   if (a->act == GTS_ACT_MASK_POS && (!tc::al16(a->aux) || a->ldaux % 4 != 0)) return false;
-  if (a->act == GTS_ACT_MASK_BITS && (!a->aux_bits || !tc::al16(a->aux_bits) || a->ld_aux_bits % 4 != 0)) return false;
+  if ((a->act == GTS_ACT_MASK_BITS || a->act == GTS_ACT_MASK_BITS_SCATTER) &&
+      (!a->aux_bits || !tc::al16(a->aux_bits) || a->ld_aux_bits % 4 != 0)) return false;
+  if (a->act == GTS_ACT_MASK_BITS_SCATTER &&
+      (!a->scatter_idx || !a->scatter_out || !tc::al16(a->scatter_idx) || a->ld_idx % 4 != 0 || a->ld_out * 4 >= ((int64_t)1 << 32)))
+    return false;
   if (a->relu_bits_out && (a->act != GTS_ACT_RELU || a->ld_bits_out < a->N / 32)) return false;
   return tc::get_encode() != nullptr;
 }
@@ -2148,6 +2190,7 @@ int gemm_nt_tcgen05(const gts_gemm_nt_args* a, cudaStream_t st) {
   p.kb2 = two ? (a->K2 + BK - 1) / BK : 0;
   p.bias = a->bias; p.bias2 = a->bias2; p.aux = a->aux; p.ldaux = a->ldaux; p.act = a->act;
   p.bits_out = a->relu_bits_out; p.ld_bits_out = a->ld_bits_out; p.aux_bits = a->aux_bits; p.ld_aux_bits = a->ld_aux_bits;
+  p.scatter_idx = a->scatter_idx; p.ld_idx = a->ld_idx; p.scatter_out = a->scatter_out; p.ld_out = a->ld_out;
   p.splits = 1;
   CUtensorMap tA1, tA2, tB1, tB2;
   if (!encode_2d(&tA1, a->A1, a->M, a->K1, a->lda1, BK, BM, rnd)) return GTS_ERR_CUDA;
@@ -2164,7 +2207,7 @@ int gemm_nt_tcgen05(const gts_gemm_nt_args* a, cudaStream_t st) {
   // Measured: same error against fp64 (2.7e-6 max on K=256 products, logits 2.6e-5 on the 8-layer stack), K=256
   // 59.8 -> 55.9 us, K=512 100.6 -> 98.3 us, training step 5.19 -> 5.10 ms.
   if (wide) return launch_ntw(tA1, tA2, tB1, tB2, p, n_work, st);
-  if (a->relu_bits_out || a->act == GTS_ACT_MASK_BITS) {
+  if (a->relu_bits_out || a->act == GTS_ACT_MASK_BITS || a->act == GTS_ACT_MASK_BITS_SCATTER) {
     set_error("gts_gemm_nt: bit-matrix masks need the 256-wide CTA-pair kernel (gts_gemm_nt_bits_supported)");
     return GTS_ERR_UNSUPPORTED;
   }

@@ -121,9 +121,10 @@ static inline float* at(void* ws, size_t off) { return reinterpret_cast<float*>(
 static int nt(const float* A1, int64_t lda1, int K1, const float* B1, int64_t ldb1, const float* A2, int64_t lda2, int K2,
               const float* B2, int64_t ldb2, const float* bias, int act, const float* aux, int64_t ldaux, float* C,
               int64_t ldc, int M, int N, int mode, gts_stream_t st, const float* bias2 = nullptr,
-              uint32_t* relu_bits_out = nullptr, const uint32_t* aux_bits = nullptr) {
+              uint32_t* relu_bits_out = nullptr, const uint32_t* aux_bits = nullptr,
+              const int32_t* scatter_idx = nullptr, float* scatter_out = nullptr) {
   gts_gemm_nt_args a;
-  a.scatter_idx = nullptr; a.ld_idx = 0; a.scatter_out = nullptr; a.ld_out = 0;
+  a.scatter_idx = scatter_idx; a.ld_idx = N; a.scatter_out = scatter_out; a.ld_out = N;
   a.relu_bits_out = relu_bits_out; a.ld_bits_out = N / 32; a.aux_bits = aux_bits; a.ld_aux_bits = N / 32;
   a.bias2 = bias2;
   a.A1 = A1; a.lda1 = lda1; a.K1 = K1; a.A2 = A2; a.lda2 = lda2; a.K2 = K2;
@@ -264,15 +265,31 @@ static int backward_range(const gts_sage_layer* layers, const gts_sage_layer_gra
     // epilogue (GTS_ACT_MASK_POS_SCATTER) is correct but slower — 320 us against 60 (GEMM) + 118 (zero-fill + scatter):
     // four epilogue warps per SM cannot keep as many REDs in flight as a full-occupancy scatter kernel.
     float* dNeigh = at(workspace, pl.P);
-    if (pl.neigh_bits[l])      // the mask (neigh > 0) as bits: 1/32 of the float operand's traffic in the epilogue
+    float* dP = at(workspace, pl.dP);
+    // dP[arg[v,k],k] += ((dZ Wn) * (neigh > 0))[v,k] straight out of the GEMM's epilogue (GTS_ACT_MASK_BITS_SCATTER): the
+    // epilogue warps keep the tile in registers, the accumulator is already back with the MMA issuer, and the REDs go
+    // out while the next item's MMAs run — no dNeigh tensor, no separate scatter pass.  Correct (tests) and MEASURED
+    // SLOWER again (round 1: 320 us with the accumulator held; round 2: 230 us against 64 + 84): 512 scattered 32-lane
+    // REDs per half tile from four warps cost the SM's LSU ~70 clk each (37 000 clk per half tile, 3x the main loop),
+    // where the stand-alone kernel spreads them over 64 resident warps.  Off unless GTS_FUSED_SCATTER=1.
+    static const bool fused_on = getenv("GTS_FUSED_SCATTER") && atoi(getenv("GTS_FUSED_SCATTER")) == 1;
+    const bool fused_scatter = fused_on && pl.neigh_bits[l] && !(csc_indptr && csc_indices);
+    if (fused_scatter) {
+      {
+        Prof prof(kProfSegBwd, stream);
+        GTS_CUDA(cudaMemsetAsync(dP, 0, sizeof(float) * (size_t)N * ly.din, as_stream(stream)));
+      }
+      GTS_TRY(nt(dZ, ldz, ly.dout, WnT, ly.dout, nullptr, 0, 0, nullptr, 0, nullptr, GTS_ACT_MASK_BITS_SCATTER, nullptr, 0,
+                 nullptr, ly.din, N, ly.din, mode, stream, nullptr, nullptr,
+                 reinterpret_cast<const uint32_t*>(at(workspace, pl.neigh_bits[l])), arg, dP));
+    } else if (pl.neigh_bits[l])      // the mask (neigh > 0) as bits: 1/32 of the float operand's traffic in the epilogue
       GTS_TRY(nt(dZ, ldz, ly.dout, WnT, ly.dout, nullptr, 0, 0, nullptr, 0, nullptr, GTS_ACT_MASK_BITS, nullptr, 0, dNeigh,
                  ly.din, N, ly.din, mode, stream, nullptr, nullptr,
                  reinterpret_cast<const uint32_t*>(at(workspace, pl.neigh_bits[l]))));
     else
       GTS_TRY(nt(dZ, ldz, ly.dout, WnT, ly.dout, nullptr, 0, 0, nullptr, 0, nullptr, GTS_ACT_MASK_POS, neigh, ly.din, dNeigh,
                  ly.din, N, ly.din, mode, stream));
-    float* dP = at(workspace, pl.dP);
-    {
+    if (!fused_scatter) {
       Prof prof(kProfSegBwd, stream);
       if (csc_indptr && csc_indices)
         GTS_TRY(gts_segmax_bwd_det(dNeigh, ly.din, arg, ly.din, csc_indptr, csc_indices, N, ly.din, dP, ly.din, stream));

@@ -54,6 +54,9 @@ enum gts_act {
                                  * bit b  <->  column 32 * (n / 32) + 4 * (b & 7) + (b >> 3); written by gts_gemm_nt
                                  * (relu_bits_out) and gts_segmax_fwd_bits.  CTA-pair tensor-core path only
                                  * (gts_gemm_nt_bits_supported). */
+  GTS_ACT_MASK_BITS_SCATTER = 5, /* GTS_ACT_MASK_POS_SCATTER with the mask as a bit matrix (aux_bits), in the epilogue of the 256-wide
+                                 * CTA-pair kernel: the masked tile never goes to memory, every non-zero element is added (fp32 RED)
+                                 * to scatter_out[scatter_idx[m,n], n] while the next item's MMAs run.  C may be NULL. */
   GTS_ACT_MASK_POS_SCATTER = 3  /* v = (aux > 0) ? acc : 0 is NOT stored to C: it is routed through saved arg-max indices,
                                  * scatter_out[scatter_idx[m,n], n] += v (fp32 RED; rows with idx < 0 and v == 0 skipped).
                                  * The backward of the neighbour max fused into the GEMM that produces its input:

@@ -92,3 +92,41 @@ def test_stack_with_bit_masks_equals_stack_with_float_masks(cuda_dev, monkeypatc
     finally:
         ops.set_stack_path(True)
         ops.set_deterministic_backward(False)
+
+
+@pytest.mark.parametrize("M,K", [(1000, 256), (90000, 256), (333, 64)])
+def test_fused_scatter_epilogue_equals_gemm_then_scatter(cuda_dev, M, K):
+    """GTS_ACT_MASK_BITS_SCATTER: dP[arg[v,k],k] += ((A W^T) * mask)[v,k] out of the GEMM epilogue == masked GEMM followed
+    by gts_segmax_bwd (up to the order of the fp32 additions)."""
+    import ctypes as C
+    lib = _lib.load()
+    N = 256
+    if not lib.gts_gemm_nt_bits_supported(M, N, _lib.GEMM_TF32X3):
+        pytest.skip("shape outside the 256-wide kernel")
+    torch.manual_seed(M)
+    A = torch.randn(M, K, device=cuda_dev)
+    W = torch.randn(N, K, device=cuda_dev)
+    act = torch.randn(M, N, device=cuda_dev)
+    # bits of (act > 0) through the product's own producer
+    bits = torch.zeros((M, N // 32), dtype=torch.int32, device=cuda_dev)
+    # producer: a ReLU GEMM whose output is relu(act) (B = identity)
+    I = torch.eye(N, device=cuda_dev)
+    out = ops.gemm_nt(act, I, act=ops.ACT_RELU, mode="tf32x3", relu_bits_out=bits)
+    assert torch.equal(out > 0, act > 0)
+    R = M
+    idx = torch.randint(-1, R, (M, N), device=cuda_dev, dtype=torch.int32)
+    # two-kernel form
+    dN = ops.gemm_nt(A, W, act=ops.ACT_MASK_BITS, aux_bits=bits, mode="tf32x3")
+    ref = ops.segmax_bwd(dN, idx, R)
+    # fused form
+    dst = torch.zeros(R, N, device=cuda_dev)
+    a = _lib.GemmNtArgs()
+    a.A1, a.lda1, a.K1 = ptr(A), K, K
+    a.B1, a.ldb1 = ptr(W), K
+    a.M, a.N, a.act, a.mode = M, N, _lib.ACT_MASK_BITS_SCATTER, _lib.GEMM_TF32X3
+    a.aux_bits, a.ld_aux_bits = ptr(bits), N // 32
+    a.scatter_idx, a.ld_idx, a.scatter_out, a.ld_out = ptr(idx), N, ptr(dst), N
+    check(lib.gts_gemm_nt(C.byref(a), stream_ptr()), "gts_gemm_nt scatter")
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    assert (dst - ref).abs().max().item() <= 2e-5 * scale
