@@ -201,3 +201,62 @@ class DevicePrefetcher:
             except StopIteration:
                 return
             self._q.append(self._stage(b))
+
+
+class StagedBatch:
+    """Static device buffers for ONE batch signature (node / edge counts per graph, tensor shapes) with copy-stream
+    staging — the input side of ``trainer.GraphedStep`` as a stand-alone helper for inference loops
+    (scripts/generate_gnn_predictions.py:43-52 moves every graph in-stream with ``.to(device)``).
+
+        sb.load_async(host_graph, tensors, copy_stream)     # H2D on the copy stream, overlaps the previous batch
+        g, dev_tensors = sb.take()                           # compute stream waits for the copies, device CSR build
+        ... enqueue the consumer ...
+        sb.release()                                         # the next load_async waits for this point
+
+    Nothing is allocated after construction except the CSR arrays of ``take`` (freed and reused by the caching
+    allocator on the consumer's own stream: no cross-stream hand-over of allocator blocks, which is what made
+    ``DevicePrefetcher`` unstable in time)."""
+
+    def __init__(self, host_graph, tensors, device):
+        if not torch.cuda.is_available():
+            raise GtsError("StagedBatch needs a CUDA device (no CPU path)")
+        dev = torch.device(device)
+        self.signature = self.signature_of(host_graph, tensors)
+        self.src = torch.empty(host_graph._src.shape, dtype=host_graph._src.dtype, device=dev)
+        self.dst = torch.empty(host_graph._dst.shape, dtype=host_graph._dst.dtype, device=dev)
+        self.node_off = host_graph._node_off.to(dev)
+        self.edge_off = host_graph._edge_off.to(dev)
+        self._node_counts, self._edge_counts = list(host_graph._node_counts), list(host_graph._edge_counts)
+        self.tensors = [torch.empty(tuple(t.shape), dtype=t.dtype, device=dev) for t in tensors]
+        self._loaded = self._done = None
+
+    @staticmethod
+    def signature_of(host_graph, tensors):
+        return (tuple(host_graph._node_counts), tuple(host_graph._edge_counts), tuple((tuple(t.shape), t.dtype) for t in tensors))
+
+    def load_async(self, host_graph, tensors, stream):
+        if self.signature_of(host_graph, tensors) != self.signature:
+            raise GtsError("StagedBatch: batch signature differs from the one the buffers were sized for")
+        if self._done is not None:
+            stream.wait_event(self._done)
+        with torch.cuda.stream(stream):
+            self.src.copy_(host_graph._src, non_blocking=True)
+            self.dst.copy_(host_graph._dst, non_blocking=True)
+            for d, t in zip(self.tensors, tensors):
+                d.copy_(t, non_blocking=True)
+        self._loaded = torch.cuda.Event()
+        self._loaded.record(stream)
+
+    def take(self):
+        from .graph import BatchedGraph
+        if self._loaded is None:
+            raise GtsError("StagedBatch.take before load_async")
+        torch.cuda.current_stream().wait_event(self._loaded)
+        self._loaded = None
+        g = BatchedGraph.from_device_edges(self.src, self.dst, self.node_off, self.edge_off, self._node_counts,
+                                           self._edge_counts)
+        return g, self.tensors
+
+    def release(self):
+        self._done = torch.cuda.Event()
+        self._done.record(torch.cuda.current_stream())

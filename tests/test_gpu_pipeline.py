@@ -111,3 +111,34 @@ def test_prefetcher_explicit_stage_next(cuda_dev):
     assert [g[0] for g in got] == [b[0] for b in batches]
     for g, b in zip(got, batches):
         assert g[1] == b[1].number_of_nodes() and abs(g[2] - float(b[2].sum())) < 1e-2 * max(1.0, abs(float(b[2].sum())))
+
+
+def test_staged_batch_equals_plain_to_device(cuda_dev):
+    """data_loader.StagedBatch: static device buffers + copy-stream staging give the same CSR / tensors as .to(device),
+    also when the buffers are re-filled while the previous contents are still being consumed."""
+    from gnn_tumor_seg_b200.data_loader import StagedBatch
+    from gnn_tumor_seg_b200 import graph as G2, networks as nets
+    gs = [synth.make_small_graph(80 + s, n_nodes=300, avg_deg=8) for s in range(2)]
+    hg = G2.batch([G2.from_edge_list(g.src, g.dst, g.n_nodes) for g in gs], pin=True)
+    variants = [torch.randn(600, 20, generator=torch.Generator().manual_seed(k)).pin_memory() for k in range(3)]
+    sb = StagedBatch(hg, [variants[0]], cuda_dev)
+    copy = torch.cuda.Stream(device=cuda_dev)
+    torch.manual_seed(0)
+    net = nets.GraphSage(20, [64], 4, "pool", 0).to(cuda_dev).eval()
+    ref_g = hg.to(cuda_dev)
+    outs = []
+    sb.load_async(hg, [variants[0]], copy)
+    for k in range(3):
+        g, (x,) = sb.take()
+        assert torch.equal(g.csr[0], ref_g.csr[0]) and torch.equal(g.csr[1], ref_g.csr[1])
+        with torch.no_grad():
+            outs.append(net(g, x).clone())
+        sb.release()
+        if k + 1 < 3:
+            sb.load_async(hg, [variants[k + 1]], copy)          # must wait for the release point above
+    torch.cuda.synchronize()
+    for k in range(3):
+        with torch.no_grad():
+            assert torch.equal(outs[k], net(ref_g, variants[k].to(cuda_dev)))
+    with pytest.raises(Exception):
+        sb.load_async(hg, [torch.zeros(5, 20).pin_memory()], copy)
