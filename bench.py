@@ -567,6 +567,15 @@ def run_ours(args):
     ncu = load_ncu_traffic()
     kern["segmax_fwd"]["traffic"] = traffic_of(ncu, "segmax_fwd_pipe")
     kern["segmax_bwd"]["traffic"] = traffic_of(ncu, "segmax_bwd_vec")
+    for key_, needle_ in (("segmax_fwd", "segmax_fwd_pipe"), ("segmax_bwd", "segmax_bwd_vec")):
+        for nm, d_ in ncu.items():       # what actually bounds them (committed ncu capture, profiles/r02_segmax_ncu.md)
+            if needle_ in nm and "l1_data_pipe_pct" in d_:
+                kern[key_]["ncu"] = {k2: d_.get(k2) for k2 in ("duration_us", "dram_pct", "lts_pct", "l1_data_pipe_pct", "l1_hit_pct",
+                                                              "issue_active_pct", "stall_long_scoreboard", "stall_lg_throttle")}
+    kern["segmax_fwd"]["note"] = ("HBM fraction on compulsory bytes; the busiest units are the L1 data pipe (E x 1 KB of gathers cross it, "
+                                  "hit or miss) and the issue slots - see the ncu block")
+    kern["segmax_bwd"]["note"] = ("dense random gradient + zero-fill; HBM fraction on the 3*N*D compulsory bytes; bound by the L2 atomic "
+                                  "path - see the ncu block; in the step half of the gradient is zero and skipped (step_breakdown)")
     kern["gemm_concat_k512"]["traffic"] = traffic_of(ncu, "gemm_x3ntw_kernel") if args.mode == "tf32x3" else None
     if args.mode == "tf32x3":
         for nm, d_ in ncu.items():           # tensor-pipe utilisation of the same ncu capture (profiles/r02_ncu_traffic.json)
