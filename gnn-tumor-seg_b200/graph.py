@@ -74,6 +74,16 @@ class BatchedGraph:
             self._zero_in_deg = bool(n > 0 and int(self.in_degrees().min()) == 0)
         return self._zero_in_deg
 
+    def has_duplicate_edges(self):
+        """True if some (src, dst) pair occurs more than once inside a graph (a multigraph).  Graphs that come from the
+        reference's networkx ``Graph`` objects never do.  The deterministic arg-max backward (gts_segmax_bwd_det walks
+        the out-edge lists) counts a duplicated edge once per copy, the atomic form once: it needs a simple graph."""
+        if self._src is None:
+            raise ops._lib.GtsError("has_duplicate_edges needs the host edge lists")
+        s, d = self._global_edges_host()
+        key = s * np.int64(max(self.number_of_nodes(), 1)) + d
+        return bool(np.unique(key).size != key.size)
+
     def _global_edges_host(self):
         off = np.repeat(self._node_off.numpy()[:-1].astype(np.int64), self._edge_counts)
         return self._src.numpy().astype(np.int64) + off, self._dst.numpy().astype(np.int64) + off

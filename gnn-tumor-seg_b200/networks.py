@@ -169,10 +169,12 @@ class GraphSage(nn.Module):
         self.layers.append(SAGEConv(layer_sizes[-1], n_classes, aggregator_type, feat_drop=0, activation=None))
 
     def _stack_fast_path_ok(self):
+        # the whole-stack backward takes dlogits as the gradient of the last layer's OUTPUT: an activation there (never
+        # in the reference, model/networks.py:30) goes through the per-layer path, which applies its mask
         return all(l._aggre_type == "pool" and l.norm is None
                    and (l.feat_drop.p == 0 or not self.training)
                    and (l.activation is None or l.activation is F.relu or l.activation is torch.relu)
-                   for l in self.layers)
+                   for l in self.layers) and self.layers[-1].activation is None
 
     def forward(self, graph, features):
         if self._stack_fast_path_ok() and ops.use_stack_path():

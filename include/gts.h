@@ -200,7 +200,9 @@ GTS_API int gts_segmax_bwd(const float* dNeigh, int64_t ldd, const int32_t* argm
                    gts_stream_t stream);
 
 /* Deterministic form: transposed gather over the out-edge CSC.
- * dP[u,k] = sum over out-edges (u->v) with argmax[v,k]==u of dNeigh[v,k]. */
+ * dP[u,k] = sum over out-edges (u->v) with argmax[v,k]==u of dNeigh[v,k].
+ * Needs a SIMPLE graph: a duplicated (u,v) edge is counted once per copy here and once by gts_segmax_bwd
+ * (BatchedGraph.has_duplicate_edges() checks; graphs from the reference's networkx Graph objects are simple). */
 GTS_API int gts_segmax_bwd_det(const float* dNeigh, int64_t ldd, const int32_t* argmax, int64_t ldarg,
                        const int32_t* csc_indptr, const int32_t* csc_indices,
                        int32_t n_nodes, int32_t D, float* dP, int64_t lddp, gts_stream_t stream);

@@ -154,3 +154,12 @@ def test_overlap_helpers_fail_loudly_without_cuda():
         DevicePrefetcher([], "cuda")
     with pytest.raises(GtsError):
         project.VolumeDownloader()
+
+
+def test_has_duplicate_edges():
+    import numpy as np
+    from gnn_tumor_seg_b200 import graph as G
+    a = G.from_edge_list(np.array([0, 1, 1, 2]), np.array([1, 0, 2, 1]), 3)
+    b = G.from_edge_list(np.array([0, 1, 0, 2]), np.array([1, 0, 1, 1]), 3)
+    assert not a.has_duplicate_edges() and b.has_duplicate_edges()
+    assert not G.batch([a, a]).has_duplicate_edges() and G.batch([a, b]).has_duplicate_edges()
