@@ -42,6 +42,7 @@ class GemmNtArgs(C.Structure):
         ("scatter_out", C.c_void_p), ("ld_out", C.c_int64),
         ("relu_bits_out", C.c_void_p), ("ld_bits_out", C.c_int64),
         ("aux_bits", C.c_void_p), ("ld_aux_bits", C.c_int64),
+        ("zero_fill", C.c_void_p), ("zero_fill_bytes", C.c_size_t),
     ]
 
 
@@ -102,6 +103,8 @@ _SIGNATURES = {
                                       c_i32p, C.c_int64, C.c_void_p, C.c_int64, c_stream]),
     "gts_segmax_bwd": (C.c_int, [c_f32p, C.c_int64, c_i32p, C.c_int64, C.c_int32, C.c_int32, c_f32p, C.c_int64,
                                  C.c_int32, c_stream]),
+    "gts_segmax_bwd_add": (C.c_int, [c_f32p, C.c_int64, c_i32p, C.c_int64, C.c_int32, C.c_int32, c_f32p, C.c_int64,
+                                     c_stream]),
     "gts_segmax_bwd_det": (C.c_int, [c_f32p, C.c_int64, c_i32p, C.c_int64, c_i32p, c_i32p, C.c_int32, C.c_int32,
                                      c_f32p, C.c_int64, c_stream]),
     "gts_segsum_fwd": (C.c_int, [c_f32p, C.c_int64, c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_f32p,

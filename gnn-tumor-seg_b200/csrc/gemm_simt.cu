@@ -475,6 +475,12 @@ int gts_gemm_nt(const gts_gemm_nt_args* a, gts_stream_t stream) {
     return GTS_ERR_UNSUPPORTED;
   }
   cudaStream_t st = as_stream(stream);
+  if (a->zero_fill && a->zero_fill_bytes) {
+    GTS_CHECK_ARG((reinterpret_cast<uintptr_t>(a->zero_fill) & 15u) == 0 && a->zero_fill_bytes % 16 == 0, "gts_gemm_nt: zero_fill must be 16-byte aligned and sized");
+    // the 256-wide kernel clears it with its spare warps (same condition as its dispatch); anything else: memset first
+    const bool wide = a->mode == GTS_GEMM_TF32X3 && gemm_nt_bits_supported(a->M, a->N, a->mode) && gemm_nt_tcgen05_supported(a);
+    if (!wide) GTS_CUDA(cudaMemsetAsync(a->zero_fill, 0, a->zero_fill_bytes, st));
+  }
   if (a->mode == GTS_GEMM_FP32) return gemm_nt_simt(a, st);
   if (a->mode == GTS_GEMM_TF32 || a->mode == GTS_GEMM_TF32X3) {
     if (gemm_nt_tcgen05_supported(a)) return gemm_nt_tcgen05(a, st);

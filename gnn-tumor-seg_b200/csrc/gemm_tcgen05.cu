@@ -226,6 +226,7 @@ struct Params {
   const uint32_t* aux_bits; int64_t ld_aux_bits;      // wide NT kernel, GTS_ACT_MASK_BITS: the mask as a bit matrix
   const int32_t* scatter_idx; int64_t ld_idx;         // wide NT kernel, GTS_ACT_MASK_BITS_SCATTER: arg-max rows [M, N]
   float* scatter_out; int64_t ld_out;                 //   and the zero-filled destination the masked tile is added into
+  uint4* zero_fill; unsigned long long zero_n16;      // wide NT kernel: side job of the two spare warps (16-byte units)
   long long* trace;        // GTS_TRACE builds only: per-CTA clock64 records of gemm_x3ntw_kernel (tools/gemm_trace.py)
   int dbg;                 // GTS_TRACE builds only: ablation switches
 };
@@ -1817,7 +1818,18 @@ gemm_x3ntw_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         if (lane == 0) { GTS_TR(tr_item, 4, clock64()); GTS_TR(tr_item, 5, tr_ready); }
       }
     }
-  }   // warps 2, 3: idle
+  } else if (p.zero_fill != nullptr) {
+    // ======================= warps 2, 3: side job — clear a buffer the NEXT kernels need zeroed =======================
+    // (the whole-stack backward hands the next layer's dP here: 92 MB of stores ride under a tensor-bound main loop
+    // instead of a 16 us memset pass between two kernels; plain coalesced 16-byte stores, 512 B per warp instruction)
+    const unsigned long long stride = (unsigned long long)gridDim.x * 64ull;
+    unsigned long long i = (unsigned long long)blockIdx.x * 64ull + (unsigned long long)((warp - 2) * 32 + lane);
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (; i + 3ull * stride < p.zero_n16; i += 4ull * stride) {
+      p.zero_fill[i] = z; p.zero_fill[i + stride] = z; p.zero_fill[i + 2ull * stride] = z; p.zero_fill[i + 3ull * stride] = z;
+    }
+    for (; i < p.zero_n16; i += stride) p.zero_fill[i] = z;
+  }
   } else if (warp < 8) {
     // ======================= A split -> TMEM (own 128 rows), two half-k-block slots per stage =======================
     setmaxnreg_dec<L::REGS_ASPLIT>();
@@ -2191,6 +2203,8 @@ int gemm_nt_tcgen05(const gts_gemm_nt_args* a, cudaStream_t st) {
   p.bias = a->bias; p.bias2 = a->bias2; p.aux = a->aux; p.ldaux = a->ldaux; p.act = a->act;
   p.bits_out = a->relu_bits_out; p.ld_bits_out = a->ld_bits_out; p.aux_bits = a->aux_bits; p.ld_aux_bits = a->ld_aux_bits;
   p.scatter_idx = a->scatter_idx; p.ld_idx = a->ld_idx; p.scatter_out = a->scatter_out; p.ld_out = a->ld_out;
+  // side job (gts_gemm_nt_args.zero_fill): only the 256-wide kernel has spare warps; gts_gemm_nt issued a memset otherwise
+  if (wide && a->zero_fill) { p.zero_fill = reinterpret_cast<uint4*>(a->zero_fill); p.zero_n16 = a->zero_fill_bytes >> 4; }
   p.splits = 1;
   CUtensorMap tA1, tA2, tB1, tB2;
   if (!encode_2d(&tA1, a->A1, a->M, a->K1, a->lda1, BK, BM, rnd)) return GTS_ERR_CUDA;

@@ -13,7 +13,7 @@ struct StackPlan {
   int L = 0;
   int64_t N = 0;
   size_t neigh[kMaxLayers], arg[kMaxLayers], out[kMaxLayers];
-  size_t P = 0, g0 = 0, g1 = 0, dP = 0, gemm_ws = 0, colsum_ws = 0, dlogits = 0;
+  size_t P = 0, g0 = 0, g1 = 0, dP = 0, dP2 = 0, gemm_ws = 0, colsum_ws = 0, dlogits = 0;
   size_t wnT[kMaxLayers], wsT[kMaxLayers], wpT[kMaxLayers];      // transposed weights of every layer (one batched launch)
   // ReLU masks as bit matrices (1 bit per element): neigh_bits[l] = (neigh_l > 0) written by the seg-max forward,
   // out_bits[l] = (out_l > 0) written by the concat GEMM's epilogue; 0 = not available for that layer (float mask then)
@@ -21,6 +21,13 @@ struct StackPlan {
   size_t gemm_ws_bytes = 0, colsum_ws_bytes = 0;
   size_t total = 0;
 };
+
+// The dh GEMM of layer l+1 clears layer l's dP with its spare warps (gts_gemm_nt_args.zero_fill) instead of a memset
+// pass in front of every scatter; GTS_ZERO_IN_GEMM=0 keeps the memsets (A/B runs) and the single dP buffer.
+static bool zero_in_gemm() {
+  static const bool on = !(getenv("GTS_ZERO_IN_GEMM") && atoi(getenv("GTS_ZERO_IN_GEMM")) == 0);
+  return on;
+}
 
 static bool make_plan(const gts_sage_layer* layers, int L, int64_t N, bool training, int mode, StackPlan& pl) {
   if (L < 1 || L > StackPlan::kMaxLayers) return false;
@@ -53,6 +60,8 @@ static bool make_plan(const gts_sage_layer* layers, int L, int64_t N, bool train
     pl.g0 = take(n * max_dim * 4);       // backward: dZ / dh ping-pong
     pl.g1 = take(n * max_dim * 4);
     pl.dP = take(n * max_din * 4);
+    // second dP: layer l scatters into dP[l & 1] while layer l+1's dh GEMM (the last reader of the other one) clears it
+    pl.dP2 = zero_in_gemm() ? take(n * max_din * 4) : pl.dP;
     for (int l = 0; l < L; ++l) {
       pl.wnT[l] = take((size_t)layers[l].din * layers[l].dout * 4);
       pl.wsT[l] = take((size_t)layers[l].din * layers[l].dout * 4);
@@ -122,8 +131,10 @@ static int nt(const float* A1, int64_t lda1, int K1, const float* B1, int64_t ld
               const float* B2, int64_t ldb2, const float* bias, int act, const float* aux, int64_t ldaux, float* C,
               int64_t ldc, int M, int N, int mode, gts_stream_t st, const float* bias2 = nullptr,
               uint32_t* relu_bits_out = nullptr, const uint32_t* aux_bits = nullptr,
-              const int32_t* scatter_idx = nullptr, float* scatter_out = nullptr) {
-  gts_gemm_nt_args a;
+              const int32_t* scatter_idx = nullptr, float* scatter_out = nullptr, void* zero_fill = nullptr,
+              size_t zero_fill_bytes = 0) {
+  gts_gemm_nt_args a{};
+  a.zero_fill = zero_fill; a.zero_fill_bytes = zero_fill_bytes;
   a.scatter_idx = scatter_idx; a.ld_idx = N; a.scatter_out = scatter_out; a.ld_out = N;
   a.relu_bits_out = relu_bits_out; a.ld_bits_out = N / 32; a.aux_bits = aux_bits; a.ld_aux_bits = N / 32;
   a.bias2 = bias2;
@@ -238,6 +249,7 @@ static int backward_range(const gts_sage_layer* layers, const gts_sage_layer_gra
     Prof prof(kProfTranspose, stream);
     if (tb.n > 0) GTS_TRY(launch_transpose_batch(tb, as_stream(stream)));
   }
+  bool dp_cleared = false;       // this layer's dP was zeroed by the previous (upper) layer's dh GEMM
   for (int l = layer_hi - 1; l >= layer_lo; --l) {
     const gts_sage_layer& ly = layers[l];
     const gts_sage_layer_grads& g = grads[l];
@@ -265,7 +277,8 @@ static int backward_range(const gts_sage_layer* layers, const gts_sage_layer_gra
     // epilogue (GTS_ACT_MASK_POS_SCATTER) is correct but slower — 320 us against 60 (GEMM) + 118 (zero-fill + scatter):
     // four epilogue warps per SM cannot keep as many REDs in flight as a full-occupancy scatter kernel.
     float* dNeigh = at(workspace, pl.P);
-    float* dP = at(workspace, pl.dP);
+    float* dP = at(workspace, (l & 1) ? pl.dP2 : pl.dP);
+    const bool det = csc_indptr && csc_indices;       // the gather form writes every element: nothing to clear
     // dP[arg[v,k],k] += ((dZ Wn) * (neigh > 0))[v,k] straight out of the GEMM's epilogue (GTS_ACT_MASK_BITS_SCATTER): the
     // epilogue warps keep the tile in registers, the accumulator is already back with the MMA issuer, and the REDs go
     // out while the next item's MMAs run — no dNeigh tensor, no separate scatter pass.  Correct (tests) and MEASURED
@@ -273,12 +286,12 @@ static int backward_range(const gts_sage_layer* layers, const gts_sage_layer_gra
     // REDs per half tile from four warps cost the SM's LSU ~70 clk each (37 000 clk per half tile, 3x the main loop),
     // where the stand-alone kernel spreads them over 64 resident warps.  Off unless GTS_FUSED_SCATTER=1.
     static const bool fused_on = getenv("GTS_FUSED_SCATTER") && atoi(getenv("GTS_FUSED_SCATTER")) == 1;
-    const bool fused_scatter = fused_on && pl.neigh_bits[l] && !(csc_indptr && csc_indices);
+    const bool fused_scatter = fused_on && pl.neigh_bits[l] && !det;
+    if (!det && !dp_cleared && N > 0) {
+      Prof prof(kProfSegBwd, stream);
+      GTS_CUDA(cudaMemsetAsync(dP, 0, sizeof(float) * (size_t)N * ly.din, as_stream(stream)));
+    }
     if (fused_scatter) {
-      {
-        Prof prof(kProfSegBwd, stream);
-        GTS_CUDA(cudaMemsetAsync(dP, 0, sizeof(float) * (size_t)N * ly.din, as_stream(stream)));
-      }
       GTS_TRY(nt(dZ, ldz, ly.dout, WnT, ly.dout, nullptr, 0, 0, nullptr, 0, nullptr, GTS_ACT_MASK_BITS_SCATTER, nullptr, 0,
                  nullptr, ly.din, N, ly.din, mode, stream, nullptr, nullptr,
                  reinterpret_cast<const uint32_t*>(at(workspace, pl.neigh_bits[l])), arg, dP));
@@ -291,11 +304,12 @@ static int backward_range(const gts_sage_layer* layers, const gts_sage_layer_gra
                  ly.din, N, ly.din, mode, stream));
     if (!fused_scatter) {
       Prof prof(kProfSegBwd, stream);
-      if (csc_indptr && csc_indices)
+      if (det)
         GTS_TRY(gts_segmax_bwd_det(dNeigh, ly.din, arg, ly.din, csc_indptr, csc_indices, N, ly.din, dP, ly.din, stream));
       else
-        GTS_TRY(gts_segmax_bwd(dNeigh, ly.din, arg, ly.din, N, ly.din, dP, ly.din, N, stream));
+        GTS_TRY(gts_segmax_bwd_add(dNeigh, ly.din, arg, ly.din, N, ly.din, dP, ly.din, stream));
     }
+    dp_cleared = false;
     {
       Prof prof(kProfTn, stream);
       GTS_TRY(gts_gemm_tn_colsum(dP, ly.din, h, ldh, g.dWp, ly.din, ly.din, ly.din, N, mode, g.dbp, gws, pl.gemm_ws_bytes, stream));
@@ -309,13 +323,22 @@ static int backward_range(const gts_sage_layer* layers, const gts_sage_layer_gra
       else { dh = at(workspace, ((n_layers - 1 - l) & 1) ? pl.g1 : pl.g0); lddh = ly.din; }
       // dh = (dZ Ws + dP' Wp) * (h > 0): h is the ReLU output of layer l-1 (no mask for the input features)
       const bool mask = l > 0 && layers[l - 1].relu != 0;
+      // side job: clear the NEXT layer's dP (the other buffer; this GEMM reads dP[l & 1]) — see zero_in_gemm()
+      void* zf = nullptr;
+      size_t zf_bytes = 0;
+      if (l > layer_lo && !det && pl.dP2 != pl.dP && N > 0 && ((size_t)N * layers[l - 1].din) % 4 == 0) {
+        zf = at(workspace, ((l - 1) & 1) ? pl.dP2 : pl.dP);
+        zf_bytes = sizeof(float) * (size_t)N * layers[l - 1].din;
+        dp_cleared = true;
+      }
       if (mask && pl.out_bits[l - 1])
         GTS_TRY(nt(dZ, ldz, ly.dout, WsT, ly.dout, dP, ly.din, ly.din, WpT, ly.din, nullptr, GTS_ACT_MASK_BITS, nullptr, 0,
                    dh, lddh, N, ly.din, mode, stream, nullptr, nullptr,
-                   reinterpret_cast<const uint32_t*>(at(workspace, pl.out_bits[l - 1]))));
+                   reinterpret_cast<const uint32_t*>(at(workspace, pl.out_bits[l - 1])), nullptr, nullptr, zf, zf_bytes));
       else
         GTS_TRY(nt(dZ, ldz, ly.dout, WsT, ly.dout, dP, ly.din, ly.din, WpT, ly.din, nullptr,
-                   mask ? GTS_ACT_MASK_POS : GTS_ACT_NONE, mask ? h : nullptr, ldh, dh, lddh, N, ly.din, mode, stream));
+                   mask ? GTS_ACT_MASK_POS : GTS_ACT_NONE, mask ? h : nullptr, ldh, dh, lddh, N, ly.din, mode, stream,
+                   nullptr, nullptr, nullptr, nullptr, nullptr, zf, zf_bytes));
     }
   }
   return GTS_OK;

@@ -886,21 +886,13 @@ int gts_segmax_fwd_bits(const float* P, int64_t ldp, const int32_t* indptr, cons
                                       pos_bits, ld_bits);
 }
 
-int gts_segmax_bwd(const float* dNeigh, int64_t ldd, const int32_t* argmax, int64_t ldarg,
-                   int32_t n_nodes, int32_t D, float* dP, int64_t lddp, int32_t n_src_rows,
-                   gts_stream_t stream) {
-  GTS_CHECK_ARG(n_nodes >= 0 && D >= 0 && n_src_rows >= 0, "gts_segmax_bwd: negative size");
-  if (n_src_rows == 0 || D == 0) return GTS_OK;
-  GTS_CHECK_ARG(dP != nullptr, "gts_segmax_bwd: dP is null");
-  GTS_CHECK_ARG(lddp >= D, "gts_segmax_bwd: lddp < D");
+int gts_segmax_bwd_add(const float* dNeigh, int64_t ldd, const int32_t* argmax, int64_t ldarg,
+                       int32_t n_nodes, int32_t D, float* dP, int64_t lddp, gts_stream_t stream) {
+  GTS_CHECK_ARG(n_nodes >= 0 && D >= 0, "gts_segmax_bwd_add: negative size");
+  if (n_nodes == 0 || D == 0) return GTS_OK;
+  GTS_CHECK_ARG(dNeigh && argmax && dP, "gts_segmax_bwd_add: null pointer");
+  GTS_CHECK_ARG(lddp >= D, "gts_segmax_bwd_add: lddp < D");
   cudaStream_t st = as_stream(stream);
-  if (lddp == D) {
-    GTS_CUDA(cudaMemsetAsync(dP, 0, sizeof(float) * (size_t)n_src_rows * D, st));
-  } else {
-    GTS_CUDA(cudaMemset2DAsync(dP, sizeof(float) * lddp, 0, sizeof(float) * D, n_src_rows, st));
-  }
-  if (n_nodes == 0) return GTS_OK;
-  GTS_CHECK_ARG(dNeigh && argmax, "gts_segmax_bwd: null pointer");
   const bool vec_ok = (D % 4 == 0) && (ldd % 4 == 0) && (ldarg % 4 == 0) && aligned16(dNeigh) && aligned16(argmax);
   const int threads = 256;
   if (vec_ok) {
@@ -918,6 +910,24 @@ int gts_segmax_bwd(const float* dNeigh, int64_t ldd, const int32_t* argmax, int6
   }
   GTS_LAUNCH_CHECK();
   return GTS_OK;
+}
+
+int gts_segmax_bwd(const float* dNeigh, int64_t ldd, const int32_t* argmax, int64_t ldarg,
+                   int32_t n_nodes, int32_t D, float* dP, int64_t lddp, int32_t n_src_rows,
+                   gts_stream_t stream) {
+  GTS_CHECK_ARG(n_nodes >= 0 && D >= 0 && n_src_rows >= 0, "gts_segmax_bwd: negative size");
+  if (n_src_rows == 0 || D == 0) return GTS_OK;
+  GTS_CHECK_ARG(dP != nullptr, "gts_segmax_bwd: dP is null");
+  GTS_CHECK_ARG(lddp >= D, "gts_segmax_bwd: lddp < D");
+  cudaStream_t st = as_stream(stream);
+  if (lddp == D) {
+    GTS_CUDA(cudaMemsetAsync(dP, 0, sizeof(float) * (size_t)n_src_rows * D, st));
+  } else {
+    GTS_CUDA(cudaMemset2DAsync(dP, sizeof(float) * lddp, 0, sizeof(float) * D, n_src_rows, st));
+  }
+  if (n_nodes == 0) return GTS_OK;
+  GTS_CHECK_ARG(dNeigh && argmax, "gts_segmax_bwd: null pointer");
+  return gts_segmax_bwd_add(dNeigh, ldd, argmax, ldarg, n_nodes, D, dP, lddp, stream);
 }
 
 int gts_segmax_bwd_det(const float* dNeigh, int64_t ldd, const int32_t* argmax, int64_t ldarg,

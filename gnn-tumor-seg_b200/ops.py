@@ -141,8 +141,10 @@ def edge_perm_compose(eid_csr, eid_csc):
 # dense contractions
 # ---------------------------------------------------------------------------
 def gemm_nt(A1, B1, A2=None, B2=None, bias=None, act=ACT_NONE, aux=None, mode=None, out=None, bias2=None,
-            relu_bits_out=None, aux_bits=None):
+            relu_bits_out=None, aux_bits=None, zero_fill=None):
     """act(A1 @ B1.T + A2 @ B2.T + bias); B* in nn.Linear layout [out,in].
+    zero_fill: an unrelated contiguous tensor the call also clears (gts_gemm_nt_args.zero_fill: spare warps of the
+    256-wide kernel, a memset otherwise).
     relu_bits_out (int32 [M, N/32], with ACT_RELU): receives the bit matrix of (C > 0); aux_bits (with ACT_MASK_BITS): the
     mask as such a bit matrix (layout: include/gts.h GTS_ACT_MASK_BITS) — 256-wide tensor-core path only."""
     require_cuda(A1, B1, A2, B2, bias, aux)
@@ -188,6 +190,10 @@ def gemm_nt(A1, B1, A2=None, B2=None, bias=None, act=ACT_NONE, aux=None, mode=No
         require_cuda(aux_bits)
         assert aux_bits.dtype == torch.int32 and tuple(aux_bits.shape) == (M, N // 32) and aux_bits.is_contiguous()
         a.aux_bits, a.ld_aux_bits = ptr(aux_bits), N // 32
+    if zero_fill is not None:
+        require_cuda(zero_fill)
+        assert zero_fill.is_contiguous()
+        a.zero_fill, a.zero_fill_bytes = ptr(zero_fill), zero_fill.numel() * zero_fill.element_size()
     a.M, a.N, a.act = M, N, act
     a.mode = _gemm_mode if mode is None else (GEMM_MODES[mode] if isinstance(mode, str) else mode)
     check(lib.gts_gemm_nt(C.byref(a), stream_ptr()), "gts_gemm_nt")

@@ -130,6 +130,11 @@ typedef struct gts_gemm_nt_args {
   float* scatter_out; int64_t ld_out;           /* GTS_ACT_MASK_POS_SCATTER: destination [rows,N], zero-filled */
   uint32_t* relu_bits_out; int64_t ld_bits_out; /* optional with GTS_ACT_RELU: bit matrix [M, ld_bits_out words] of (C > 0) */
   const uint32_t* aux_bits; int64_t ld_aux_bits; /* GTS_ACT_MASK_BITS: the mask, [M, ld_aux_bits words] */
+  /* Optional side job: clear zero_fill[0, zero_fill_bytes) (16-byte aligned, a multiple of 16 bytes, must not overlap
+   * any operand or output of this call).  The 256-wide CTA-pair kernel does it with its two spare warps while the tiles
+   * run (the whole-stack backward clears the next layer's dP this way instead of a separate memset pass); every other
+   * kernel choice issues a plain memset on the stream first.  Either way the buffer is zero when the call's work is done. */
+  void* zero_fill; size_t zero_fill_bytes;
 } gts_gemm_nt_args;
 
 GTS_API int gts_gemm_nt(const gts_gemm_nt_args* args, gts_stream_t stream);
@@ -198,6 +203,11 @@ GTS_API int gts_segmax_fwd_bits(const float* P, int64_t ldp, const int32_t* indp
 GTS_API int gts_segmax_bwd(const float* dNeigh, int64_t ldd, const int32_t* argmax, int64_t ldarg,
                    int32_t n_nodes, int32_t D, float* dP, int64_t lddp, int32_t n_src_rows,
                    gts_stream_t stream);
+
+/* The scatter half of gts_segmax_bwd alone: dP[arg[v,k], k] += dNeigh[v,k] into a buffer the caller initialised
+ * (zero for the plain backward; gts_sage_backward has the previous layer's GEMM clear it as a side job). */
+GTS_API int gts_segmax_bwd_add(const float* dNeigh, int64_t ldd, const int32_t* argmax, int64_t ldarg,
+                       int32_t n_nodes, int32_t D, float* dP, int64_t lddp, gts_stream_t stream);
 
 /* Deterministic form: transposed gather over the out-edge CSC.
  * dP[u,k] = sum over out-edges (u->v) with argmax[v,k]==u of dNeigh[v,k].

@@ -53,7 +53,8 @@ def test_argument_validation_without_gpu(built_lib):
 def test_gemm_args_struct_layout():
     from gnn_tumor_seg_b200._lib import GemmNtArgs
     # matches the C struct under the SysV x86-64 ABI (natural alignment)
-    assert ctypes.sizeof(GemmNtArgs) == 208
+    assert ctypes.sizeof(GemmNtArgs) == 224
     assert GemmNtArgs.K1.offset == 16 and GemmNtArgs.A2.offset == 24 and GemmNtArgs.mode.offset == 132 and GemmNtArgs.bias2.offset == 136
     assert GemmNtArgs.scatter_idx.offset == 144 and GemmNtArgs.ld_out.offset == 168
     assert GemmNtArgs.relu_bits_out.offset == 176 and GemmNtArgs.ld_aux_bits.offset == 200
+    assert GemmNtArgs.zero_fill.offset == 208 and GemmNtArgs.zero_fill_bytes.offset == 216

@@ -130,3 +130,39 @@ def test_fused_scatter_epilogue_equals_gemm_then_scatter(cuda_dev, M, K):
     torch.cuda.synchronize()
     scale = ref.abs().max().item()
     assert (dst - ref).abs().max().item() <= 2e-5 * scale
+
+
+@pytest.mark.parametrize("M,N,K,mode", [(3000, 256, 256, "tf32x3"), (3000, 256, 256, "fp32"), (100, 64, 32, "tf32x3"),
+                                        (90000, 256, 512, "tf32x3")])
+def test_gemm_zero_fill_side_job(cuda_dev, M, N, K, mode):
+    """gts_gemm_nt_args.zero_fill: the buffer is zero after the call whichever kernel ran (spare warps of the 256-wide
+    kernel, memset in front of the others), the product is unchanged, neighbours of the buffer are untouched."""
+    torch.manual_seed(7)
+    A, B = torch.randn(M, K, device=cuda_dev), torch.randn(N, K, device=cuda_dev)
+    ref = ops.gemm_nt(A, B, mode=mode)
+    guard = 1024
+    n = M * N + 12                                        # not a multiple of the kernel's 4-way unrolled stride
+    buf = torch.full((n + 2 * guard,), 3.5, device=cuda_dev)
+    out = ops.gemm_nt(A, B, mode=mode, zero_fill=buf[guard:guard + n])
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    assert int(torch.count_nonzero(buf[guard:guard + n])) == 0
+    assert bool((buf[:guard] == 3.5).all()) and bool((buf[guard + n:] == 3.5).all())
+
+
+def test_segmax_bwd_add_accumulates(cuda_dev):
+    """gts_segmax_bwd_add = the scatter half of gts_segmax_bwd: adds into what the caller put there."""
+    lib = _lib.load()
+    g = synth.make_small_graph(5, n_nodes=2000, avg_deg=9, isolated=3)
+    dg = G.from_edge_list(g.src, g.dst, g.n_nodes).to(cuda_dev)
+    N, D = g.n_nodes, 128
+    torch.manual_seed(2)
+    P = torch.randn(N, D, device=cuda_dev)
+    indptr, indices = dg.csr
+    neigh, arg = ops.segmax_fwd(P, indptr, indices)
+    dN = torch.randn(N, D, device=cuda_dev)
+    dP = ops.segmax_bwd(dN, arg, N)
+    base = torch.randn(N, D, device=cuda_dev)
+    acc = base.clone()
+    check(lib.gts_segmax_bwd_add(ptr(dN), D, ptr(arg), D, N, D, ptr(acc), D, stream_ptr()), "gts_segmax_bwd_add")
+    torch.testing.assert_close(acc - base, dP, rtol=0, atol=2e-5)
