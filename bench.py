@@ -503,6 +503,17 @@ def run_ours(args):
 
     # ---- per-kernel breakdown and live roofline of the dominant + aggregation kernels ----
     # rank 0 only from here on: no collectives (the other ranks are already waiting at the final barrier)
+    peer_ex = getattr(trainer, "peer", None)
+    dp_exchange, peer_status = None, None
+    if world > 1:
+        if peer_ex is not None:
+            dp_exchange = ("gradient arena exchanged over NVLink peer memory (CUDA IPC): gts_peer_publish + ONE kernel that reads every "
+                           "rank's copy, sums in rank order and applies AdamW (gts_peer_allreduce_adamw), both inside the captured "
+                           "graph of the step — no NCCL on the data path")
+            peer_status = peer_ex.status()
+        else:
+            dp_exchange = ("bucketed NCCL all-reduce (async, top layers' bucket beside the lower layers' backward); CUDA-graph "
+                           "segments with the eager collectives between them")
     trainer.world_size = 1
 
     def autograd_step():           # the same kernels through the per-op wrappers (attributable launches)
@@ -670,15 +681,15 @@ def run_ours(args):
                 "mode": e2e_mode,
                 "loss_read": {"graph": "every step's loss D2H-copied into pinned memory behind the step and read by the host one "
                                        "step later (while the next step runs); H2D of step i+1 on a copy stream; step replayed "
-                                       "from a CUDA graph (trainer.GraphedStep; N > 1: graph segments around the eager all-reduces)",
+                                       "from a CUDA graph (trainer.GraphedStep; N > 1: see dp_exchange)",
                               "eager": "every step's loss D2H-copied into pinned memory and read by the host one step later; "
                                        "H2D of step i+1 on a copy stream into static device buffers (SAGE) / in-stream .to(device) (GAT)",
                               "sync": "one blocking loss.item() per step"}[e2e_mode]},
         "gpu_launches": int(launches),
         "eager_ms_per_step": ms_eager,
         "value_path": (("CUDA-graph replay of the step (trainer.GraphedStep, incl. the device CSR build), inputs resident in "
-                        "their static device buffers" + ("" if world == 1 else "; data parallel: captured segments with the eager "
-                        "bucketed NCCL all-reduces between them")) if gsteps is not None else "eager trainer step, inputs and CSR resident"),
+                        "their static device buffers" + ("" if world == 1 else "; data parallel: " + dp_exchange))
+                       if gsteps is not None else "eager trainer step, inputs and CSR resident"),
         "roofline": roofline,
         "kernels": kern,
         "step_breakdown": share,
@@ -687,6 +698,9 @@ def run_ours(args):
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if world > 1:
+        line["dp_exchange"] = dp_exchange
+        if peer_status is not None:
+            line["dp_peer_status"] = {"epochs": peer_status[0], "error": peer_status[1]}
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
     return line

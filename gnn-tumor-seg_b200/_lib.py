@@ -72,6 +72,15 @@ class SageStepArgs(C.Structure):
                 ("mode", C.c_int32), ("normalize", C.c_int32), ("bwd_layer_lo", C.c_int32), ("reserved", C.c_int32)]
 
 
+MAX_PEERS = 16
+PEER_HANDLE_BYTES = 64
+
+
+class PeerComm(C.Structure):
+    """struct gts_peer_comm (include/gts.h)."""
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("n", C.c_int64), ("base", C.c_void_p * MAX_PEERS)]
+
+
 # name -> (restype, argtypes); mirrors include/gts.h one to one
 _SIGNATURES = {
     "gts_version": (C.c_int, []),
@@ -156,6 +165,15 @@ _SIGNATURES = {
     "gts_adamw_step": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_float, C.c_float, C.c_float,
                                  C.c_float, C.c_float, C.c_int32, C.c_float, c_f32p, c_stream]),
     "gts_adamw_step_dev": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, c_f32p, C.c_float, c_f32p, c_stream]),
+    "gts_peer_buffer_bytes": (C.c_size_t, [C.c_int64]),
+    "gts_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
+    "gts_peer_free": (C.c_int, [C.c_void_p]),
+    "gts_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "gts_peer_close": (C.c_int, [C.c_void_p]),
+    "gts_peer_publish": (C.c_int, [C.POINTER(PeerComm), c_f32p, c_stream]),
+    "gts_peer_allreduce_adamw": (C.c_int, [C.POINTER(PeerComm), c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p, c_f32p,
+                                           C.c_int64, C.c_int32, c_stream]),
+    "gts_peer_status": (C.c_int, [C.POINTER(PeerComm), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

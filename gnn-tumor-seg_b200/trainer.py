@@ -174,7 +174,7 @@ class SageTrainer:
     """
 
     def __init__(self, net, class_weights, lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8,
-                 process_group=None, n_buckets=2, optimizer=None, data_parallel=None):
+                 process_group=None, n_buckets=2, optimizer=None, data_parallel=None, peer=None):
         from .networks import GraphSage
         if not isinstance(net, GraphSage) or not all(l._aggre_type == "pool" for l in net.layers):
             raise GtsError("SageTrainer: a GraphSage('pool') network is required")
@@ -193,7 +193,15 @@ class SageTrainer:
         self.world_size = (dist.get_world_size(process_group)
                            if data_parallel is not False and dist.is_available() and dist.is_initialized() else 1)
         self.L = len(net.layers)
-        self.buckets = plan_buckets(self.arena.group_off, self.L, n_buckets if self.world_size > 1 else 1)
+        # Data parallel: the gradient exchange over NVLink peer memory fused with AdamW (peer.PeerExchange, both
+        # launches inside the captured step) where the ranks can map each other's buffers; otherwise — or with
+        # peer=False / GTS_DP_PEER=0 — the bucketed NCCL all-reduce beside the backward.  Collective decision.
+        self.peer = None
+        if self.world_size > 1 and peer is not False and isinstance(self.optimizer, FusedAdamW):
+            from .peer import PeerExchange
+            self.peer = PeerExchange.try_create(self.arena.grads.numel(), process_group)
+        use_buckets = self.world_size > 1 and self.peer is None
+        self.buckets = plan_buckets(self.arena.group_off, self.L, n_buckets if use_buckets else 1)
         self._ws = None
         self._logits = None
         self._bias_scratch = None
@@ -266,7 +274,7 @@ class SageTrainer:
 
     # ---- the step ----------------------------------------------------------------------------------------
     def forward_backward(self, graph, feats, labels):
-        """Forward + CE + backward (+ all-reduce): gradients land in the arena; returns the loss (0-d device tensor).
+        """Forward + CE + backward (+ gradient exchange): gradients land in the arena; returns the loss (0-d device tensor).
         Single device: gradients of the weighted mean.  Data parallel: un-normalised sums, divided by the GLOBAL
         denominator inside the optimiser launch (``optimizer.step(grad_denom=trainer.denominator)``)."""
         lib = _lib.load()
@@ -275,6 +283,14 @@ class SageTrainer:
             a = self._step_args(graph, feats, labels, True, 0)
             check(lib.gts_sage_step(C.byref(a), stream_ptr()), "gts_sage_step")
             ops._count(23 * L + 3)
+            return self.arena.extra[0] / self.arena.extra[1]
+        if self.peer is not None:
+            # data parallel over peer memory: whole backward, publish the arena, sum every rank's copy in rank order
+            a = self._step_args(graph, feats, labels, False, 0)
+            check(lib.gts_sage_step(C.byref(a), stream_ptr()), "gts_sage_step")
+            self.peer.publish(self.arena.grads)
+            self.peer.allreduce(self.arena.grads)
+            ops._count(23 * L + 5)
             return self.arena.extra[0] / self.arena.extra[1]
         # data parallel: top bucket's layers first, its all-reduce runs while the lower layers back-propagate
         hi0, lo0, _, _ = self.buckets[0]
@@ -318,6 +334,17 @@ class SageTrainer:
         return self.arena.extra[1:2]
 
     def step(self, graph, feats, labels):
+        if self.world_size > 1 and self.peer is not None:
+            # forward + CE + backward, then TWO launches: publish the arena, and one pass that reads every rank's
+            # copy over NVLink, sums in rank order, divides by the global loss denominator and applies AdamW
+            opt, ar = self.optimizer, self.arena
+            a = self._step_args(graph, feats, labels, False, 0)
+            check(_lib.load().gts_sage_step(C.byref(a), stream_ptr()), "gts_sage_step")
+            opt._sync_lr()
+            self.peer.publish(ar.grads)
+            self.peer.allreduce_adamw(ar.grads, ar.total, ar.params, opt.exp_avg, opt.exp_avg_sq, opt.hyper, ar.total + 1)
+            ops._count(23 * self.L + 5)
+            return ar.extra[0] / ar.extra[1]
         loss = self.forward_backward(graph, feats, labels)
         self.optimizer.step(grad_denom=self.denominator if self.world_size > 1 else None)
         return loss
@@ -358,7 +385,8 @@ class GraphedStep:
         self.launches_per_replay = ops.launch_counter["n"] - n0        # kernels one replay stands for
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
-        if trainer.world_size == 1:
+        if trainer.world_size == 1 or trainer.peer is not None:
+            # (data parallel over peer memory: the exchange kernels carry their own cross-GPU flags — one graph)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self._body(BatchedGraph)

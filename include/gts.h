@@ -454,6 +454,67 @@ GTS_API int gts_adamw_step(float* param, const float* grad, float* exp_avg, floa
 GTS_API int gts_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                        float* hyper, float grad_scale, const float* grad_denom, gts_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * Data-parallel gradient exchange over NVLink peer memory, fused with the
+ * optimiser (the reference trains on one device,
+ * model/gnn_model.py:23,41-47 — whole graphs per rank is the natural shard).
+ *
+ * One process per GPU.  Every rank owns ONE exchange buffer in its own HBM
+ *   [ 256-byte header | staging buffer 0: n floats | staging buffer 1: n floats ]
+ * that the other ranks of the box map through CUDA IPC (NVLink / NVSwitch
+ * peer access).  A step is two launches, both capturable in a CUDA graph:
+ *   gts_peer_publish          copies the rank's un-normalised gradient arena
+ *                             (+ the two loss sums behind it) into staging
+ *                             buffer (epoch & 1) and then raises the rank's
+ *                             flag in EVERY peer's header (release, system scope);
+ *   gts_peer_allreduce_adamw  waits until every rank's flag has reached the
+ *                             epoch (acquire, bounded spin), reads all ranks'
+ *                             staging buffers over NVLink, sums them in rank
+ *                             order (identical bits on every rank), writes the
+ *                             sums back to the gradient arena and — apply != 0 —
+ *                             runs the AdamW update of gts_adamw_step_dev on
+ *                             sum / (summed loss denominator) in the same pass.
+ * The epoch counter lives in the header (device side), so replays of a
+ * captured graph and eager calls interleave freely; the two staging buffers
+ * alternate by epoch parity, which makes one flag exchange per step enough
+ * (a rank can run at most one step ahead of the slowest one).  A peer that
+ * never arrives sets the header's error word after ~20 s instead of hanging
+ * the GPU (gts_peer_status).
+ *
+ * gts_peer_alloc / gts_peer_free / gts_peer_open / gts_peer_close are the only
+ * entry points of this library that allocate or map device memory (an
+ * IPC-exportable buffer cannot be carved from a caller's pool).
+ * ------------------------------------------------------------------------ */
+#define GTS_MAX_PEERS 16
+#define GTS_PEER_HANDLE_BYTES 64
+
+typedef struct gts_peer_comm {
+  int32_t rank, world;            /* world <= GTS_MAX_PEERS */
+  int64_t n;                      /* floats per staging buffer (multiple of 4) */
+  void* base[GTS_MAX_PEERS];      /* base[r]: rank r's exchange buffer as mapped in THIS process
+                                   * (gts_peer_alloc for r == rank, gts_peer_open of r's handle otherwise) */
+} gts_peer_comm;
+
+GTS_API size_t gts_peer_buffer_bytes(int64_t n);
+/* cudaMalloc + zero-fill + cudaIpcGetMemHandle on the current device; handle: GTS_PEER_HANDLE_BYTES bytes to send to
+ * the other ranks (any byte transport: the host side uses torch.distributed.all_gather_object). */
+GTS_API int gts_peer_alloc(size_t bytes, void** dptr, unsigned char* handle);
+GTS_API int gts_peer_free(void* dptr);
+/* cudaIpcOpenMemHandle with lazy peer access from the current device; fails (GTS_ERR_CUDA) where the two devices have
+ * no peer path — the caller then keeps the NCCL all-reduce. */
+GTS_API int gts_peer_open(const unsigned char* handle, void** dptr);
+GTS_API int gts_peer_close(void* dptr);
+/* src: n floats (16-byte aligned). */
+GTS_API int gts_peer_publish(const gts_peer_comm* comm, const float* src, gts_stream_t stream);
+/* grads: n floats, receives the sums.  apply != 0: AdamW on the first n_params elements (param / exp_avg /
+ * exp_avg_sq / hyper as in gts_adamw_step_dev, hyper[5] incremented by the call) with the summed gradient divided by
+ * the summed element denom_index of the exchanged vector (denom_index < 0: no division). */
+GTS_API int gts_peer_allreduce_adamw(const gts_peer_comm* comm, float* grads, int64_t n_params, float* param,
+                             float* exp_avg, float* exp_avg_sq, float* hyper, int64_t denom_index, int32_t apply,
+                             gts_stream_t stream);
+/* Synchronous read of the local header: completed epochs and the error word (0 = ok, 1 = a peer's flag timed out). */
+GTS_API int gts_peer_status(const gts_peer_comm* comm, uint32_t* epoch, uint32_t* error);
+
 #ifdef __cplusplus
 }
 #endif

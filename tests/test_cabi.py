@@ -58,3 +58,19 @@ def test_gemm_args_struct_layout():
     assert GemmNtArgs.scatter_idx.offset == 144 and GemmNtArgs.ld_out.offset == 168
     assert GemmNtArgs.relu_bits_out.offset == 176 and GemmNtArgs.ld_aux_bits.offset == 200
     assert GemmNtArgs.zero_fill.offset == 208 and GemmNtArgs.zero_fill_bytes.offset == 216
+
+
+def test_peer_exchange_abi(built_lib):
+    """struct gts_peer_comm layout, buffer sizing and argument checks of the peer-memory exchange (no CUDA call)."""
+    from gnn_tumor_seg_b200 import _lib
+    lib = _lib.load()
+    assert ctypes.sizeof(_lib.PeerComm) == 16 + 8 * _lib.MAX_PEERS and _lib.PeerComm.base.offset == 16
+    assert lib.gts_peer_buffer_bytes(1000) == 256 + 2 * 1000 * 4
+    assert lib.gts_peer_buffer_bytes(1001) == 256 + 2 * 1004 * 4          # staging buffers are whole float4s
+    assert lib.gts_peer_publish(None, None, None) == 1 and b"null comm" in lib.gts_last_error()
+    c = _lib.PeerComm()
+    c.rank, c.world, c.n = 0, 40, 1024
+    assert lib.gts_peer_publish(ctypes.byref(c), None, None) == 1 and b"at most" in lib.gts_last_error()
+    c.world = 2
+    assert lib.gts_peer_allreduce_adamw(ctypes.byref(c), None, 0, None, None, None, None, -1, 0, None) == 1
+    assert b"base[0] is null" in lib.gts_last_error()

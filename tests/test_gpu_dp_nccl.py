@@ -1,7 +1,8 @@
-"""On-hardware data-parallel correctness: 2 ranks under NCCL, whole graphs per rank,
-trainer.SageTrainer's bucketed all-reduce overlapped with the backward.  After the step the gradient arenas are
-BITWISE equal across ranks and agree with the single-device step on the union batch to 1e-5 (norm-wise; the
-all-reduce and the union batch sum the same per-graph contributions in a different order).
+"""On-hardware data-parallel correctness: 2 ranks, whole graphs per rank, both gradient-exchange
+paths of trainer.SageTrainer — the bucketed NCCL all-reduce overlapped with the backward, and the NVLink peer-memory
+exchange fused with AdamW (peer.PeerExchange, csrc/peer.cu).  After the step the gradient arenas are BITWISE equal
+across ranks and agree with the single-device step on the union batch to 1e-5 (norm-wise; the exchange and the union
+batch sum the same per-graph contributions in a different order); the CUDA-graphed step equals the eager one.
 Needs >= 2 GPUs (gpurun --gpus 2); skipped otherwise."""
 import os
 import socket
@@ -20,7 +21,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, use_peer):
     import torch.distributed as dist
     from gnn_tumor_seg_b200 import graph as G, networks, ops, synth
     from gnn_tumor_seg_b200.trainer import SageTrainer
@@ -40,8 +41,15 @@ def _worker(rank, world, port, out_dir):
     w = torch.tensor(W, device=dev)
     torch.manual_seed(0)
     net = networks.GraphSage(20, [256, 256, 64], 4, "pool", 0).to(dev)
-    tr = SageTrainer(net, w, lr=1e-3, weight_decay=1e-4, n_buckets=2)
-    assert tr.world_size == world and len(tr.buckets) == 2
+    tr = SageTrainer(net, w, lr=1e-3, weight_decay=1e-4, n_buckets=2, peer=use_peer)
+    assert tr.world_size == world
+    peer_active = tr.peer is not None
+    if not use_peer:
+        assert not peer_active and len(tr.buckets) == 2
+    peer_failure = None
+    if use_peer and not peer_active:
+        from gnn_tumor_seg_b200.peer import PeerExchange
+        peer_failure = PeerExchange.last_failure
     loss = tr.forward_backward(*batch_of(list(range(rank, 4, world))))        # rank r owns graphs r, r+R, ...
     torch.cuda.synchronize()
     n = tr.arena.total
@@ -74,10 +82,13 @@ def _worker(rank, world, port, out_dir):
     for _ in range(2):
         torch.manual_seed(5)
         nets.append(networks.GraphSage(20, [256, 256, 64], 4, "pool", 0).to(dev))
-    tr_e = SageTrainer(nets[0], w, lr=1e-3, weight_decay=1e-4)
-    tr_g = SageTrainer(nets[1], w, lr=1e-3, weight_decay=1e-4)
-    gs = GraphedStep(tr_g, hg, hx, hy)                      # one eager warm-up step + capture of the segments
-    assert gs.segments is not None and len(gs.segments) == len(tr_g.buckets) + 1
+    tr_e = SageTrainer(nets[0], w, lr=1e-3, weight_decay=1e-4, peer=use_peer)
+    tr_g = SageTrainer(nets[1], w, lr=1e-3, weight_decay=1e-4, peer=use_peer)
+    gs = GraphedStep(tr_g, hg, hx, hy)                      # one eager warm-up step + capture
+    if tr_g.peer is not None:                               # peer exchange: the whole step is ONE graph
+        assert gs.graph is not None and gs.segments is None
+    else:                                                   # NCCL: segments around the eager collectives
+        assert gs.segments is not None and len(gs.segments) == len(tr_g.buckets) + 1
     le = lg = None
     for it in range(3):
         le = tr_e.step(hg.to(dev), hx.to(dev), hy.to(dev))
@@ -85,22 +96,99 @@ def _worker(rank, world, port, out_dir):
             lg = gs(hg, hx, hy)
     torch.cuda.synchronize()
     gdiff = float((tr_e.arena.params - tr_g.arena.params).abs().mean())
-    torch.save({"bitwise": bitwise, "rel": rel, "loss": float(loss), "loss1": float(loss1), "prel": prel,
+    # parameters stay bitwise equal across ranks through the fused exchange + optimiser steps
+    pg = [torch.empty_like(tr_g.arena.params) for _ in range(world)]
+    dist.all_gather(pg, tr_g.arena.params)
+    params_bitwise = all(torch.equal(pg[0], x) for x in pg[1:])
+    peer_err = [t_.peer.status() for t_ in (tr, tr_e, tr_g) if t_.peer is not None]
+    torch.save({"peer_active": peer_active, "peer_failure": peer_failure, "params_bitwise": params_bitwise,
+                "peer_status": peer_err, "bitwise": bitwise, "rel": rel, "loss": float(loss), "loss1": float(loss1), "prel": prel,
                 "graph_param_diff": gdiff, "loss_eager": float(le), "loss_graph": float(lg)},
                os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_two_rank_nccl_step_equals_single_device_union_batch(tmp_path):
+needs_two = pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2,
+                               reason="needs 2 GPUs (gpurun --gpus 2)")
+
+
+@needs_two
+@pytest.mark.parametrize("use_peer", [False, True], ids=["nccl", "peer"])
+def test_two_rank_step_equals_single_device_union_batch(tmp_path, use_peer):
     import torch.multiprocessing as mp
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), use_peer), nprocs=2, join=True)
     for r in range(2):
         d = torch.load(os.path.join(str(tmp_path), f"r{r}.pt"))
-        assert d["bitwise"], "gradient arenas differ across ranks after the all-reduce"
+        if use_peer and not d["peer_active"]:
+            pytest.skip("peer-memory exchange unavailable on this box (%s): the NCCL path is what runs" % d["peer_failure"])
+        assert d["peer_active"] == use_peer
+        for epochs, err in d["peer_status"]:
+            assert err == 0 and epochs >= 2, d          # no flag ever timed out; the self-test alone is two epochs
+        assert d["params_bitwise"], "parameters differ across ranks after the optimiser steps"
+        assert d["bitwise"], "gradient arenas differ across ranks after the exchange"
         assert d["rel"] <= 1e-5, d
         assert abs(d["loss"] - d["loss1"]) <= 1e-5 * abs(d["loss1"]), d
         assert d["prel"] <= 2e-4, d          # |lr| = 1e-3: a first AdamW step moves every element by ~lr
         assert d["graph_param_diff"] < 1e-6 and abs(d["loss_eager"] - d["loss_graph"]) <= 1e-5 * abs(d["loss_eager"]), d
+
+
+def _worker_exchange(rank, world, port, out_dir):
+    """peer.PeerExchange alone: 6 fused exchange + AdamW steps against NCCL all-reduce + gts_adamw_step_dev."""
+    import torch.distributed as dist
+    from gnn_tumor_seg_b200.peer import PeerExchange
+    from gnn_tumor_seg_b200.trainer import FusedAdamW
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", device_id=dev)
+    n_params, n = 300_004, 300_008                     # [parameters | loss sum, weight sum, pad, pad]
+    ex = PeerExchange.try_create(n)
+    out = {"active": ex is not None, "failure": PeerExchange.last_failure}
+    if ex is not None:
+        torch.manual_seed(3)
+        p0 = torch.randn(n_params, device=dev)
+        opts = []
+        for _ in range(2):                             # [0]: fused peer path, [1]: NCCL + stand-alone AdamW
+            p = torch.nn.Parameter(p0.clone())
+            opts.append((p, FusedAdamW([p], lr=1e-2, weight_decay=1e-2)))
+        worst_g, worst_p, bit_g = 0.0, 0.0, True
+        for it in range(6):
+            torch.manual_seed(100 * it + rank)
+            g = torch.randn(n, device=dev)
+            g[n_params + 1] = 2.0 + rank               # this rank's loss denominator
+            (pa, oa), (pb, ob) = opts
+            # fused path works on a vector of the exchange's length: the arena of a 300 004-element parameter + 4
+            ga = g.clone()
+            ex.publish(ga)
+            ex.allreduce_adamw(ga, n_params, oa.arena.params, oa.exp_avg, oa.exp_avg_sq, oa.hyper, n_params + 1)
+            gb = g.clone()
+            dist.all_reduce(gb)
+            ob.arena.grads[:n_params].copy_(gb[:n_params])
+            ob.step(grad_denom=gb[n_params + 1:n_params + 2])
+            torch.cuda.synchronize()
+            bit_g = bit_g and bool(torch.equal(ga, gb))
+            worst_g = max(worst_g, float((ga - gb).abs().max()))
+            worst_p = max(worst_p, float((oa.arena.params - ob.arena.params).abs().max()))
+        out.update(bit_g=bit_g, worst_g=worst_g, worst_p=worst_p, status=ex.status(),
+                   steps=(float(opts[0][1].hyper[5]), float(opts[1][1].hyper[5])))
+        ex.close()
+    torch.save(out, os.path.join(out_dir, f"x{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@needs_two
+def test_peer_exchange_fused_adamw_equals_nccl_plus_adamw(tmp_path):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker_exchange, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        d = torch.load(os.path.join(str(tmp_path), f"x{r}.pt"))
+        if not d["active"]:
+            pytest.skip("peer-memory exchange unavailable on this box (%s)" % d["failure"])
+        assert d["status"] == (8, 0), d                # 2 self-test epochs + 6 steps, no flag time-out
+        assert d["bit_g"] and d["worst_g"] == 0.0, d   # two ranks: a + b is order-independent -> identical bits
+        assert d["worst_p"] <= 2e-6, d                 # same formula as gts_adamw_step_dev; FMA contraction may differ by an ulp
+        assert d["steps"] == (6.0, 6.0), d
