@@ -43,6 +43,24 @@ struct TransposeBatch {
 };
 int launch_transpose_batch(const TransposeBatch& b, cudaStream_t st);
 
+// Deferred split-K reductions (gemm_simt.cu): while a batch is installed on the calling thread, every reduction that
+// qualifies for the wide kernel is queued instead of launched, and launch_splitk_reduce_batch runs all of them in ONE
+// launch (same kernel body and summation order as the immediate launches: identical bits).  The caller owns the
+// partial-product buffers until that launch — every deferred GEMM needs its own workspace slice.
+struct ReduceJob {
+  const float4* partial; float4* C; float4* tail;
+  int64_t stride4, main4, total4;
+  int32_t splits, blk0;              // blk0: first block of this job inside the batched grid
+};
+struct ReduceBatch {
+  static constexpr int kMaxJobs = 48;
+  int n = 0, blocks = 0;
+  ReduceJob job[kMaxJobs];
+};
+void splitk_defer_set(ReduceBatch* batch);      // nullptr: launch immediately (the default)
+ReduceBatch* splitk_defer_target();
+int launch_splitk_reduce_batch(ReduceBatch& batch, cudaStream_t st);   // launches and empties the batch
+
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
 

@@ -176,12 +176,12 @@ __global__ void splitk_reduce_vec_kernel(const float4* __restrict__ partial, int
 // all loads in flight), then warp 0 adds the four partial sums in a fixed order -> deterministic, 4x the parallelism
 // of one thread per output (a 256x256 weight gradient has only 16 384 float4 outputs).  Outputs [0, main4) go to C,
 // outputs [main4, total4) to `tail` (the fused column sums of the weight-gradient GEMM).
-__global__ void __launch_bounds__(128)
-splitk_reduce_wide_kernel(const float4* __restrict__ partial, int64_t split_stride4, int splits, int64_t main4,
-                          int64_t total4, float4* __restrict__ C, float4* __restrict__ tail) {
+__device__ __forceinline__ void splitk_reduce_wide_body(const float4* __restrict__ partial, int64_t split_stride4, int splits,
+                                                        int64_t main4, int64_t total4, float4* __restrict__ C,
+                                                        float4* __restrict__ tail, int64_t block) {
   __shared__ float4 red[3][32];
   const int o = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const int64_t i = (int64_t)blockIdx.x * 32 + o;
+  const int64_t i = block * 32 + o;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (i < total4) {
     int z = g;
@@ -205,6 +205,20 @@ splitk_reduce_wide_kernel(const float4* __restrict__ partial, int64_t split_stri
     if (i < main4) C[i] = s;
     else tail[i - main4] = s;
   }
+}
+
+__global__ void __launch_bounds__(128)
+splitk_reduce_wide_kernel(const float4* __restrict__ partial, int64_t split_stride4, int splits, int64_t main4,
+                          int64_t total4, float4* __restrict__ C, float4* __restrict__ tail) {
+  splitk_reduce_wide_body(partial, split_stride4, splits, main4, total4, C, tail, blockIdx.x);
+}
+
+// Every queued reduction of a backward range in one launch: block -> (job, block of that job), same body.
+__global__ void __launch_bounds__(128) splitk_reduce_batch_kernel(const ReduceBatch b) {
+  int j = 0;
+  while (j + 1 < b.n && (int)blockIdx.x >= b.job[j + 1].blk0) ++j;
+  const ReduceJob& q = b.job[j];
+  splitk_reduce_wide_body(q.partial, q.stride4, q.splits, q.main4, q.total4, q.C, q.tail, (int64_t)blockIdx.x - q.blk0);
 }
 
 // Column sums, wide fast path (cols % 4 == 0, cols <= 1024, 16-byte aligned rows):
@@ -319,10 +333,32 @@ bool splitk_reduce_fused_ok(int64_t rows, int64_t cols, int64_t ldc, int64_t tai
   return ldc == cols && (rows * cols) % 4 == 0 && tail_len % 4 == 0 && split_stride % 4 == 0 && al(partial) && al(C) &&
          (tail_len == 0 || al(tail));
 }
+static thread_local ReduceBatch* g_defer = nullptr;
+void splitk_defer_set(ReduceBatch* batch) { g_defer = batch; }
+ReduceBatch* splitk_defer_target() { return g_defer; }
+
+int launch_splitk_reduce_batch(ReduceBatch& b, cudaStream_t st) {
+  if (b.n > 0) {
+    splitk_reduce_batch_kernel<<<b.blocks, 128, 0, st>>>(b);
+    b.n = 0; b.blocks = 0;
+    GTS_LAUNCH_CHECK();
+  }
+  return GTS_OK;
+}
+
 void launch_splitk_reduce_fused(const float* partial, int64_t split_stride, int splits, int64_t rows, int64_t cols,
                                 float* C, float* tail, int64_t tail_len, cudaStream_t st) {
   const int64_t main4 = rows * cols / 4, total4 = main4 + tail_len / 4;
   const int blocks = (int)ceil_div<int64_t>(total4, 32);
+  if (ReduceBatch* q = g_defer) {                       // queued: the owner of the batch launches it
+    if (q->n == ReduceBatch::kMaxJobs) launch_splitk_reduce_batch(*q, st);
+    ReduceJob& j = q->job[q->n++];
+    j.partial = reinterpret_cast<const float4*>(partial); j.C = reinterpret_cast<float4*>(C);
+    j.tail = reinterpret_cast<float4*>(tail);
+    j.stride4 = split_stride / 4; j.main4 = main4; j.total4 = total4; j.splits = splits; j.blk0 = q->blocks;
+    q->blocks += blocks;
+    return;
+  }
   splitk_reduce_wide_kernel<<<blocks, 128, 0, st>>>(reinterpret_cast<const float4*>(partial), split_stride / 4, splits, main4,
                                                     total4, reinterpret_cast<float4*>(C), reinterpret_cast<float4*>(tail));
 }

@@ -19,7 +19,23 @@ struct StackPlan {
   // out_bits[l] = (out_l > 0) written by the concat GEMM's epilogue; 0 = not available for that layer (float mask then)
   size_t neigh_bits[kMaxLayers], out_bits[kMaxLayers];
   size_t gemm_ws_bytes = 0, colsum_ws_bytes = 0;
+  // deferred split-K reductions (defer_reduce()): every weight-gradient GEMM of the backward keeps its partial products
+  // in its own slice until the ONE reduction launch at the end of the layer range
+  size_t tn2_ws[kMaxLayers], tn_ws[kMaxLayers], tn2_ws_bytes[kMaxLayers], tn_ws_bytes[kMaxLayers];
+  bool defer = false;
   size_t total = 0;
+};
+
+// One split-K reduction launch per backward range instead of one to three per weight-gradient GEMM (30 launches of
+// ~7 us in the 7x256 step); GTS_DEFER_REDUCE=0 keeps the immediate launches and the single shared GEMM workspace.
+static bool defer_reduce() {
+  static const bool on = !(getenv("GTS_DEFER_REDUCE") && atoi(getenv("GTS_DEFER_REDUCE")) == 0);
+  return on;
+}
+
+struct DeferGuard {      // installs the batch on this thread for the lifetime of a backward range
+  explicit DeferGuard(ReduceBatch* b) { splitk_defer_set(b); }
+  ~DeferGuard() { splitk_defer_set(nullptr); }
 };
 
 // The dh GEMM of layer l+1 clears layer l's dP with its spare warps (gts_gemm_nt_args.zero_fill) instead of a memset
@@ -78,6 +94,18 @@ static bool make_plan(const gts_sage_layer* layers, int L, int64_t N, bool train
     pl.gemm_ws_bytes = gw; pl.colsum_ws_bytes = cw;
     pl.gemm_ws = take(gw);
     pl.colsum_ws = take(cw);
+    pl.defer = defer_reduce();
+    for (int l = 0; l < L; ++l) {
+      if (pl.defer) {
+        pl.tn2_ws_bytes[l] = gts_gemm_tn2_colsum_workspace_bytes(layers[l].dout, layers[l].din, N, mode);
+        pl.tn_ws_bytes[l] = gts_gemm_tn_colsum_workspace_bytes(layers[l].din, layers[l].din, N, mode);
+        pl.tn2_ws[l] = take(pl.tn2_ws_bytes[l]);
+        pl.tn_ws[l] = take(pl.tn_ws_bytes[l]);
+      } else {
+        pl.tn2_ws[l] = pl.tn_ws[l] = pl.gemm_ws;
+        pl.tn2_ws_bytes[l] = pl.tn_ws_bytes[l] = gw;
+      }
+    }
     pl.dlogits = take(n * layers[L - 1].dout * 4);     // gts_sage_step: gradient of the loss w.r.t. the logits
   } else {
     for (int l = 0; l < L; ++l) pl.neigh_bits[l] = pl.out_bits[l] = 0;
@@ -249,6 +277,11 @@ static int backward_range(const gts_sage_layer* layers, const gts_sage_layer_gra
     Prof prof(kProfTranspose, stream);
     if (tb.n > 0) GTS_TRY(launch_transpose_batch(tb, as_stream(stream)));
   }
+  ReduceBatch reduce_batch;
+  DeferGuard defer_guard(pl.defer ? &reduce_batch : nullptr);
+  struct BiasCopy { float* dst; const float* src; size_t bytes; };
+  BiasCopy bias_copy[StackPlan::kMaxLayers];
+  int n_bias_copy = 0;
   bool dp_cleared = false;       // this layer's dP was zeroed by the previous (upper) layer's dh GEMM
   for (int l = layer_hi - 1; l >= layer_lo; --l) {
     const gts_sage_layer& ly = layers[l];
@@ -261,16 +294,19 @@ static int backward_range(const gts_sage_layer* layers, const gts_sage_layer_gra
     const int64_t ldh = (l == 0) ? ldf : ly.din;
     const float* neigh = at(workspace, pl.neigh[l]);
     const int32_t* arg = reinterpret_cast<const int32_t*>(at(workspace, pl.arg[l]));
-    void* gws = at(workspace, pl.gemm_ws);
     // (dZ already carries this layer's ReLU mask: the consumer's epilogue applied (out > 0))
     // dWs = dZ^T h, dWn = dZ^T neigh and db = column sums of dZ: one pass over dZ in the 3xTF32 mode
     {
       Prof prof(kProfTn2, stream);
-      GTS_TRY(gts_gemm_tn2_colsum(dZ, ldz, h, ldh, neigh, ly.din, g.dWs, g.dWn, ly.din, ly.dout, ly.din, N, mode, g.db, gws,
-                                  pl.gemm_ws_bytes, stream));
+      GTS_TRY(gts_gemm_tn2_colsum(dZ, ldz, h, ldh, neigh, ly.din, g.dWs, g.dWn, ly.din, ly.dout, ly.din, N, mode, g.db,
+                                  at(workspace, pl.tn2_ws[l]), pl.tn2_ws_bytes[l], stream));
     }
-    if (g.db2 && N > 0)      // fc_neigh.bias enters the output as fc_self.bias does: same gradient, its own arena slot
-      GTS_CUDA(cudaMemcpyAsync(g.db2, g.db, sizeof(float) * (size_t)ly.dout, cudaMemcpyDeviceToDevice, as_stream(stream)));
+    if (g.db2 && N > 0) {    // fc_neigh.bias enters the output as fc_self.bias does: same gradient, its own arena slot
+      if (pl.defer)          // (db exists only after the deferred reduction: copied behind it)
+        bias_copy[n_bias_copy++] = BiasCopy{g.db2, g.db, sizeof(float) * (size_t)ly.dout};
+      else
+        GTS_CUDA(cudaMemcpyAsync(g.db2, g.db, sizeof(float) * (size_t)ly.dout, cudaMemcpyDeviceToDevice, as_stream(stream)));
+    }
     // dNeigh' = (dZ Wn) * (neigh > 0)
     const float* WnT = at(workspace, pl.wnT[l]);
     // Measured (profiles/r01_gemm_x3_pipeline.md): routing the masked tile through the arg-max from inside the GEMM
@@ -312,7 +348,8 @@ static int backward_range(const gts_sage_layer* layers, const gts_sage_layer_gra
     dp_cleared = false;
     {
       Prof prof(kProfTn, stream);
-      GTS_TRY(gts_gemm_tn_colsum(dP, ly.din, h, ldh, g.dWp, ly.din, ly.din, ly.din, N, mode, g.dbp, gws, pl.gemm_ws_bytes, stream));
+      GTS_TRY(gts_gemm_tn_colsum(dP, ly.din, h, ldh, g.dWp, ly.din, ly.din, ly.din, N, mode, g.dbp,
+                                 at(workspace, pl.tn_ws[l]), pl.tn_ws_bytes[l], stream));
     }
     if (l > 0 || dfeats) {
       const float* WsT = at(workspace, pl.wsT[l]);
@@ -340,6 +377,12 @@ static int backward_range(const gts_sage_layer* layers, const gts_sage_layer_gra
                    mask ? GTS_ACT_MASK_POS : GTS_ACT_NONE, mask ? h : nullptr, ldh, dh, lddh, N, ly.din, mode, stream,
                    nullptr, nullptr, nullptr, nullptr, nullptr, zf, zf_bytes));
     }
+  }
+  if (pl.defer) {              // every queued split-K reduction of the range in one launch, then the bias copies
+    Prof prof(kProfTn, stream);
+    GTS_TRY(launch_splitk_reduce_batch(reduce_batch, as_stream(stream)));
+    for (int i = 0; i < n_bias_copy; ++i)
+      GTS_CUDA(cudaMemcpyAsync(bias_copy[i].dst, bias_copy[i].src, bias_copy[i].bytes, cudaMemcpyDeviceToDevice, as_stream(stream)));
   }
   return GTS_OK;
 }
