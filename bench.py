@@ -33,7 +33,7 @@ IN_FEATS, N_CLASSES = 20, 4
 CLASS_W = [0.1, 1.0, 2.0, 2.0]
 N_DISTINCT_GRAPHS = 8
 WORKLOAD_SAGE = ("GraphSAGE-pool 7x256 training fwd+CE+bwd(+AdamW), batch of 6 synthetic 15k-node supervoxel RAGs per GPU "
-                 "(BASELINE configs[1]; configs[3] for N>1: whole graphs per rank + bucketed NCCL grad all-reduce)")
+                 "(BASELINE configs[1]; configs[3] for N>1: whole graphs per rank + one gradient-arena sum per step over NVLink)")
 WORKLOAD_GAT = ("GAT 4-head x256 (layer_sizes [256]*4, heads [4,4,4,4], residuals [F,F,T,F]) training fwd+CE+bwd(+AdamW), "
                 "batch of 6 synthetic 15k-node supervoxel RAGs per GPU (BASELINE configs[2])")
 # BASELINE configs[2] / SURVEY §8 a5: GAT 4-head x256

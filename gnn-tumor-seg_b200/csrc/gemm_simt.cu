@@ -595,9 +595,14 @@ int gts_gemm_tn2_colsum(const float* A, int64_t lda, const float* B1, int64_t ld
       gemm_tn2_tcgen05_supported(A, lda, B1, ldb1, B2, ldb2, Mo, No, K, mode))
     return gemm_tn2_tcgen05(A, lda, B1, ldb1, B2, ldb2, C1, C2, ldc, Mo, No, K, colsum_out, workspace, workspace_bytes,
                             as_stream(stream));
+  // two products through ONE workspace: the first one's split-K reduction must run before the second product
+  // overwrites the partial sums, so neither is deferred (narrow first / last layer shapes only)
+  ReduceBatch* const deferred = splitk_defer_target();
+  splitk_defer_set(nullptr);
   int rc = gts_gemm_tn_colsum(A, lda, B1, ldb1, C1, ldc, Mo, No, K, mode, colsum_out, workspace, workspace_bytes, stream);
-  if (rc != GTS_OK) return rc;
-  return gts_gemm_tn(A, lda, B2, ldb2, C2, ldc, Mo, No, K, mode, workspace, workspace_bytes, stream);
+  if (rc == GTS_OK) rc = gts_gemm_tn(A, lda, B2, ldb2, C2, ldc, Mo, No, K, mode, workspace, workspace_bytes, stream);
+  splitk_defer_set(deferred);
+  return rc;
 }
 
 size_t gts_colsum_workspace_bytes(int64_t rows, int32_t cols) {
