@@ -9,8 +9,11 @@
                      count live on the device, so the launch can be replayed from a CUDA graph.
 * ``SageTrainer``  — forward + CE + backward as ONE library call (``gts_sage_step``) on caller-owned workspace and
                      arenas (nothing allocated per step), the optimiser launch behind it; data-parallel: the
-                     backward is split in two ranges and the finished range's bucket is all-reduced (NCCL, async)
-                     while the other range runs, the loss denominator is folded into the AdamW launch;
+                     gradient arena is exchanged over NVLink peer memory and summed, normalised and applied by ONE
+                     kernel (``peer.PeerExchange``: gts_peer_publish + gts_peer_allreduce_adamw, both inside the
+                     captured step); where the ranks cannot map each other's memory the backward is split in two
+                     ranges and the finished range's bucket is all-reduced (NCCL, async) while the other range
+                     runs, the loss denominator folded into the AdamW launch;
                      ``GraphedStep`` captures the whole step (device CSR build included) into a CUDA graph for
                      fixed-shape batches.
 
