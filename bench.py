@@ -515,6 +515,7 @@ def run_ours(args):
                            "rank's copy, sums in rank order and applies AdamW (gts_peer_allreduce_adamw), both inside the captured "
                            "graph of the step — no NCCL on the data path")
             peer_status = peer_ex.status()
+            trainer.check_exchange()          # a timed-out flag wait invalidates the timed region: fail loudly
         else:
             dp_exchange = ("bucketed NCCL all-reduce (async, top layers' bucket beside the lower layers' backward); CUDA-graph "
                            "segments with the eager collectives between them")

@@ -331,6 +331,18 @@ class SageTrainer:
         end = self.arena.total + 2 if i == 0 else g_hi
         return dist.all_reduce(self.arena.grads[g_lo:end], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
 
+    def check_exchange(self):
+        """Raise GtsError when a flag wait of the peer-memory exchange ran into its bound (a rank fell more than 10 s
+        behind or died: that step summed a stale staging buffer).  Synchronises the device — call it where the host
+        reads results anyway (end of an epoch, before a checkpoint).  No-op without a peer exchange."""
+        if self.peer is None:
+            return
+        epochs, err = self.peer.status()
+        if err:
+            raise GtsError(f"peer-memory gradient exchange: a rank's flag timed out (after {epochs} completed exchanges); "
+                           "the parameters of this rank are no longer in sync — restart from the last checkpoint "
+                           "(GTS_DP_PEER=0 selects the NCCL all-reduce)")
+
     @property
     def denominator(self):
         """sum of the class weights of the (global) batch — 1-element device tensor."""
