@@ -62,6 +62,15 @@ def load_ncu_traffic():
     return out
 
 
+def gat_traffic(table, kernel):
+    """DRAM bytes of one GAT step's launches of an edge kernel: 4 hidden layers (H x F = 4 x 256, the <2,..> instance)
+    + the output layer (<1,..>), from the per-launch ncu figures; None without a capture."""
+    wide, narrow = traffic_of(table, kernel + "<2"), traffic_of(table, kernel + "<1")
+    if wide is None or narrow is None:
+        return None
+    return (len(GAT_LAYER_SIZES)) * wide + narrow
+
+
 def traffic_of(table, *needles):
     for name, d in table.items():
         if all(n in name for n in needles) and "dram_bytes" in d:
@@ -606,8 +615,13 @@ def run_ours(args):
                 gbs_ = byt / (breakdown[nm]["ms"] * 1e-3) / 1e9
                 kern[nm[4:]] = {"ms": breakdown[nm]["ms"], "calls": breakdown[nm]["calls"], "bound": "hbm", "achieved": gbs_,
                                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs_ / peaks["hbm_gbs"], "alg_bytes": byt,
-                                "traffic": traffic_of(ncu, nm[4:] + "_kernel"),
-                                "note": "all 5 layers' launches of this kernel; gathers of 1 KB head slices come from L1/L2"}
+                                "traffic": gat_traffic(ncu, nm[4:] + "_kernel"),
+                                "note": "all 5 layers' launches of this kernel (traffic: 4 x the wide <2,..> launch + the "
+                                        "narrow output layer's, ncu); gathers of 1 KB head slices come from L1/L2"}
+                nc = next((d_ for k_, d_ in ncu.items() if nm[4:] + "_kernel<2" in k_), None)
+                if nc:                       # the wide launch's counters (profiles/r02_gat_tn_ncu.md): issue-bound, not HBM
+                    kern[nm[4:]]["ncu"] = {k_: nc.get(k_) for k_ in ("duration_us", "dram_pct", "lts_pct", "l1_data_pipe_pct",
+                                                                     "l1_hit_pct", "issue_active_pct", "stall_long_scoreboard")}
     tot = sum(v["ms"] for v in breakdown.values()) or 1.0
     share = {k: {"ms": round(v["ms"], 4), "calls": v["calls"], "share": round(v["ms"] / tot, 4)}
              for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])}
