@@ -101,6 +101,8 @@ def _worker(rank, world, port, out_dir, use_peer):
     dist.all_gather(pg, tr_g.arena.params)
     params_bitwise = all(torch.equal(pg[0], x) for x in pg[1:])
     peer_err = [t_.peer.status() for t_ in (tr, tr_e, tr_g) if t_.peer is not None]
+    for t_ in (tr, tr_e, tr_g, tr1):
+        t_.check_exchange()                                 # raises on a timed-out flag wait; no-op without peers
     torch.save({"peer_active": peer_active, "peer_failure": peer_failure, "params_bitwise": params_bitwise,
                 "peer_status": peer_err, "bitwise": bitwise, "rel": rel, "loss": float(loss), "loss1": float(loss1), "prel": prel,
                 "graph_param_diff": gdiff, "loss_eager": float(le), "loss_graph": float(lg)},
