@@ -74,3 +74,29 @@ def test_peer_exchange_abi(built_lib):
     c.world = 2
     assert lib.gts_peer_allreduce_adamw(ctypes.byref(c), None, 0, None, None, None, None, -1, 0, None) == 1
     assert b"base[0] is null" in lib.gts_last_error()
+
+
+def test_integration_doc_stub_matches_the_binding():
+    """INTEGRATION.md's Level-2 ctypes stub is what a reference maintainer would paste: its struct must be the library's
+    struct (same fields, types and order as _lib.GemmNtArgs, which test_gemm_args_struct_layout pins to the header) and
+    its positional constructor calls must fill every field."""
+    import ast
+    from gnn_tumor_seg_b200 import _lib
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", doc, re.S)
+    stub = next(b for b in blocks if "class GemmNtArgs" in b)
+    tree = ast.parse(stub)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "GemmNtArgs")
+    fields_node = next(n for n in cls.body if isinstance(n, ast.Assign) and n.targets[0].id == "_fields_")
+    doc_fields = [(e.elts[0].value, getattr(ctypes, e.elts[1].attr)) for e in fields_node.value.elts]
+    lib_fields = list(_lib.GemmNtArgs._fields_)         # (ctypes aliases: c_int64 is c_long here)
+    assert doc_fields == lib_fields
+    calls = [n for n in ast.walk(tree) if isinstance(n, ast.Call) and getattr(n.func, "id", "") == "GemmNtArgs"]
+    assert len(calls) == 2 and all(len(c.args) == len(lib_fields) for c in calls)
+    # the one argtypes list the stub spells out
+    a = next(n for n in ast.walk(tree) if isinstance(n, ast.Assign) and isinstance(n.targets[0], ast.Attribute)
+             and n.targets[0].attr == "argtypes")
+    assert len(a.value.elts) == len(_lib._SIGNATURES["gts_segmax_fwd"][1])
+    # every entry point of the header is named in the document's table
+    for s in _declared_symbols():
+        assert s in doc or (s.endswith("_workspace_bytes") and "gts_*_workspace_bytes" in doc), s
