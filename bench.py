@@ -233,7 +233,7 @@ def run_reference(args):
         opt.zero_grad()
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
 
     for _ in range(args.warmup):
         step()
