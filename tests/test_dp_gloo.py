@@ -48,7 +48,11 @@ def _worker(rank, world, port, out_dir):
         csr, feats, labels = _make(mine)
         tr = dp.DataParallelTrainer(net, W, loss_sums_fn=_cpu_loss_sums)
         loss = tr.forward_backward(csr, feats, labels)
-        torch.save({"loss": loss, "grads": tr.grads.clone(), "extra": tr.extra.clone()},
+        # the peer-memory exchange is an NVLink / CUDA-IPC mechanism: under gloo every rank gets None before any
+        # collective of its own is issued (no hang, no half-built exchange) and the all-reduce path above is what runs
+        from gnn_tumor_seg_b200.peer import PeerExchange
+        peer_none = PeerExchange.try_create(1024) is None
+        torch.save({"loss": loss, "grads": tr.grads.clone(), "extra": tr.extra.clone(), "peer_none": peer_none},
                    os.path.join(out_dir, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()
@@ -83,6 +87,7 @@ def test_world2_equals_single_process_union_batch(tmp_path):
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     r0 = torch.load(tmp_path / "r0.pt"); r1 = torch.load(tmp_path / "r1.pt")
     assert torch.equal(r0["grads"], r1["grads"]) and torch.equal(r0["loss"], r1["loss"])     # bitwise equal across ranks
+    assert r0["peer_none"] and r1["peer_none"]
     # single process, union batch in any graph order: weighted mean over ALL nodes
     net = _net()
     csr, feats, labels = _make(list(range(6)))
